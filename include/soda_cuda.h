@@ -1,0 +1,124 @@
+/* C ABI of a compiled SODA stencil program on B200 (one shared library per
+ * .soda program, built by `sodac --cuda-kernel K.cu --cuda-host H.cu` + nvcc).
+ *
+ * The library exports two faces:
+ *
+ * 1. The reference's own entry point, unchanged, with C++ linkage exactly as
+ *    the reference's generated header declares it
+ *    (reference src/soda/codegen/xilinx/header.py:57-60, defined for the FPGA
+ *    by host.print_entrance, src/soda/codegen/xilinx/host.py:931-945):
+ *
+ *        int <app>(buffer_t *var_<in0>_buffer, ..., buffer_t *var_<out0>_buffer,
+ *                  ..., const char *xclbin);
+ *
+ *    so the reference's generated test harness `<app>_test`
+ *    (host.py:984-1167) links against it unmodified.  `xclbin` is an opaque
+ *    string for the FPGA flow; here it is ignored (NULL or "" are fine).
+ *
+ * 2. The `extern "C"` functions below, which are what a foreign-function
+ *    binding (ctypes: soda/cuda.py; cgo/JNI stubs: INTEGRATION.md) loads.
+ *    Symbol names are fixed; the program identity is queried at run time.
+ *
+ * All arrays are dense with dimension 0 fastest: stride[0] = 1,
+ * stride[d] = extent[0] * ... * extent[d-1], as the reference harness sets
+ * them up (host.py:1011-1020).  Return value 0 is success; negative values
+ * follow the Halide numbering the reference host uses (host.py:118-133),
+ * e.g. -3 = bad_elem_size, -12 = buffer_argument_is_null, -23 =
+ * device_run_failed.  Nothing here falls back to the CPU: without a CUDA
+ * device every compute entry returns -19 (no_device_interface).
+ */
+#ifndef SODA_CUDA_H_
+#define SODA_CUDA_H_
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Legacy Halide buffer_t, byte-for-byte the struct the reference emits
+ * (header.py:32-49): sizeof 72; offsets dev 0, host 8, extent 16, stride 32,
+ * min 48, elem_size 64.  `host` is caller-owned memory; `dev`, unused by the
+ * reference host, may carry a CUDA device pointer (then host may be NULL and
+ * no copies are made).  host == NULL && dev == 0 requests bounds-query mode
+ * (host.py:204-252): extents/strides are filled in and nothing is computed. */
+#ifndef BUFFER_T_DEFINED
+#define BUFFER_T_DEFINED
+typedef struct buffer_t {
+  uint64_t dev;
+  uint8_t* host;
+  int32_t extent[4];
+  int32_t stride[4];
+  int32_t min[4];
+  int32_t elem_size;
+  bool host_dirty;
+  bool dev_dirty;
+  uint8_t _padding[10 - sizeof(void*)];
+} buffer_t;
+#endif /* BUFFER_T_DEFINED */
+
+/* What the last soda_cuda_run / soda_cuda_run_device call did. */
+typedef struct soda_cuda_stats_t {
+  double kernel_ms;      /* device time of all launches (CUDA events) */
+  double h2d_ms;         /* host->device copies, 0 for device buffers */
+  double d2h_ms;
+  int64_t cells;         /* prod(dims) */
+  int32_t iterate;
+  int32_t launches;      /* kernels launched */
+  int32_t depth;         /* iterations fused by the main launches */
+  int32_t used_tma;      /* 1: TMA input path, 0: plain-load path */
+  int32_t blocks;        /* thread blocks of the last launch */
+  int32_t threads;
+  int32_t smem_bytes;
+  int32_t reserved;
+} soda_cuda_stats_t;
+
+/* ---- program identity (what `sodac` compiled into this library) ---------- */
+const char* soda_cuda_app_name(void);
+int soda_cuda_dim(void);
+int soda_cuda_iterate(void);        /* the program's `iterate` */
+int soda_cuda_num_inputs(void);
+int soda_cuda_num_outputs(void);
+/* kind 0: input, 1: output.  Type is the haoda name, e.g. "float", "uint16". */
+const char* soda_cuda_tensor_name(int kind, int index);
+const char* soda_cuda_tensor_type(int kind, int index);
+int soda_cuda_tensor_elem_size(int kind, int index);
+/* Offsets of the inputs read by one output cell after `iterate` iterations:
+ * lo[d] <= offset <= hi[d]; outputs are defined on [-lo, dims - hi). */
+int soda_cuda_window(int iterate, int32_t lo[4], int32_t hi[4]);
+
+/* ---- running ---------------------------------------------------------------
+ * soda_cuda_run: the generic form of `<app>()` — n_in input and n_out output
+ * buffer_t pointers in program order.  Synchronous: outputs are complete (in
+ * `host`, or in `dev` for device buffers) on return.  Cells outside the
+ * valid region are written as 0. */
+int soda_cuda_run(buffer_t* const* inputs, buffer_t* const* outputs,
+                  const char* config);
+
+/* Device-resident dense arrays, `iterate` iterations (0: the program's own),
+ * enqueued on `stream` (a cudaStream_t; NULL = default stream), asynchronous.
+ * Inputs are not modified. */
+int soda_cuda_run_device(const void* const* inputs, void* const* outputs,
+                         const int32_t* dims, int iterate, void* stream);
+
+/* One kernel launch: `depth` fused iterations (must be a compiled depth, see
+ * soda_cuda_depths) producing streamed planes [row_begin, row_end) of the
+ * outputs from the full input arrays; cells outside [valid_lo, valid_hi) are
+ * stored as 0.  For slab-partitioned multi-GPU runs (soda/cuda.py). */
+int soda_cuda_launch(int depth, const void* const* inputs,
+                     void* const* outputs, const int32_t* dims, int row_begin,
+                     int row_end, const int32_t* valid_lo,
+                     const int32_t* valid_hi, void* stream);
+/* Fills up to `max` compiled depths (decreasing); returns how many exist. */
+int soda_cuda_depths(int32_t* depths, int max);
+
+const soda_cuda_stats_t* soda_cuda_last_stats(void);
+/* Releases cached device buffers and streams. */
+void soda_cuda_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SODA_CUDA_H_ */

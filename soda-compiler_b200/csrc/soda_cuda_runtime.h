@@ -1,0 +1,106 @@
+// Host runtime behind the generated `<app>()` entry point and the C ABI in
+// include/soda_cuda.h.  Hand-written; one copy is linked into every
+// per-program library next to the generated kernel and host files.
+//
+// It replaces, for the GPU, what the reference's generated OpenCL host does
+// between receiving `buffer_t`s and returning results
+// (reference src/soda/codegen/xilinx/host.py:186-929 `<app>_wrapped`): argument
+// checks and bounds-query mode (:204-252), device setup (:350-561), moving
+// data to the device in the kernel's layout (:629-686 — here a plain dense
+// copy, no tiling/burst/bank packing), launching and timing (:775-804), and
+// copying the valid region back (:823-901).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "soda_cuda.h"
+
+namespace soda {
+
+constexpr int kRtMaxDim = 4;
+constexpr int kRtMaxTensors = 8;
+
+// One compiled streaming kernel: `depth` iterations fused (plan.Schedule).
+struct KernelVariant {
+  int depth;
+  int threads;
+  int vec;
+  int tile[kRtMaxDim - 1];      // block tile in the non-streamed dims
+  int own[kRtMaxDim - 1];       // cells of the tile this block stores
+  int halo_lo[kRtMaxDim - 1];   // tile origin = tile index * own - halo_lo
+  int lead;                     // steps before the first owned plane
+  int out_delay;                // steps after the last owned plane
+  int smem_bytes;
+  int box0;                     // TMA box extent along dim 0
+  int boxes_per_row;
+  const void* kernel_tma;       // __global__ void(StreamArgs), TMA input path
+  const void* kernel_plain;     // same, plain-load input path
+};
+
+struct ProgramDesc {
+  const char* app_name;
+  int dim;
+  int iterate;
+  int n_in, n_out;
+  const char* in_name[kRtMaxTensors];
+  const char* out_name[kRtMaxTensors];
+  const char* in_type[kRtMaxTensors];    // haoda type names
+  const char* out_type[kRtMaxTensors];
+  int in_elem[kRtMaxTensors];            // bytes per element
+  int out_elem[kRtMaxTensors];
+  // window[(n * 2 + side) * kRtMaxDim + d]: bounding box (side 0: min offset,
+  // side 1: max offset) of the inputs read by outputs after n iterations,
+  // n = 0..iterate.  Defines the valid region [-min, dims - max).
+  const int* window;
+  // STENCIL_DIM_d of the reference host (host.py:1188-1189): window extents.
+  int stencil_dim[kRtMaxDim];
+  int n_variants;
+  const KernelVariant* variants;         // sorted by decreasing depth
+};
+
+// Result codes: the Halide error numbering the reference host uses
+// (host.py:118-133).
+enum {
+  kSuccess = 0,
+  kGenericError = -1,
+  kBadElemSize = -3,
+  kAccessOutOfBounds = -4,
+  kBufferExtentsTooLarge = -6,
+  kOutOfMemory = -11,
+  kBufferArgumentIsNull = -12,
+  kCopyToHostFailed = -14,
+  kCopyToDeviceFailed = -15,
+  kDeviceMallocFailed = -16,
+  kDeviceSyncFailed = -17,
+  kNoDeviceInterface = -19,
+  kInternalError = -22,
+  kDeviceRunFailed = -23,
+};
+
+// `<app>(buffer_t*..., const char*)`: host or device buffers, bounds query.
+int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
+                buffer_t* const* outputs, const char* config);
+
+// All `iterate` iterations on device-resident dense arrays, asynchronously on
+// `stream`.  Inputs are not modified.
+int run_device(const ProgramDesc& prog, const void* const* inputs,
+               void* const* outputs, const int32_t* dims, int iterate,
+               cudaStream_t stream);
+
+// One launch of the variant with `depth` fused iterations producing streamed
+// planes [row_begin, row_end) of the outputs; cells outside
+// [valid_lo, valid_hi) are stored as 0.  Building block for slab-partitioned
+// multi-GPU runs, where the caller owns ping-pong buffers and halo exchange.
+int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
+           void* const* outputs, const int32_t* dims, int row_begin,
+           int row_end, const int32_t* valid_lo, const int32_t* valid_hi,
+           cudaStream_t stream);
+
+const soda_cuda_stats_t* last_stats();
+
+// Frees the cached device buffers.
+void release_all();
+
+}  // namespace soda

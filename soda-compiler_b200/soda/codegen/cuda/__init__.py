@@ -1,0 +1,225 @@
+"""CUDA (sm_100a) backend of sodac: ``--cuda-kernel`` / ``--cuda-host``.
+
+Same plugin shape as the reference's Xilinx OpenCL backend
+(reference src/soda/codegen/xilinx/opencl.py:75-95 ``add_arguments``, :97-136
+``print_code``; wired at src/sodac:12,66,127): ``add_arguments(group)`` adds the
+backend's options to the sodac parser and ``print_code(stencil, args)`` writes
+each requested artefact to a file or, for ``-``, to stdout.  The stencil is
+not modified.  Unsupported programs raise ``haoda.util.SemanticError`` (sodac
+exits 1).
+
+Artefacts
+  --cuda-kernel FILE   the streaming kernels (.cu) + their variant table
+  --cuda-host FILE     program descriptor, ``<app>()`` entry, C ABI (.cpp/.cu)
+  --cuda-header FILE   ``<app>.h`` as the reference emits it (buffer_t +
+                       prototype), for callers of ``<app>()``
+
+Build: ``nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -shared``
+over the two files plus csrc/soda_cuda_runtime.cu (``soda.cuda.build`` does it).
+"""
+import math
+import shutil
+import sys
+import tempfile
+
+from haoda import util
+from soda.codegen.cuda import host as host_mod
+from soda.codegen.cuda import kernel as kernel_mod
+from soda.codegen.cuda import plan as plan_mod
+
+SUPPORTED_TYPES = {
+    'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32', 'int64',
+    'float', 'float32', 'double', 'float64'}
+SMEM_LIMIT = 227 * 1024
+
+
+def add_arguments(parser):
+  parser.add_argument(
+      '--cuda-kernel', type=str, dest='cuda_kernel_file', metavar='file',
+      help='CUDA kernel code (sm_100a) for the B200 backend')
+  parser.add_argument(
+      '--cuda-host', type=str, dest='cuda_host_file', metavar='file',
+      help='host C++ code for the B200 backend: defines <app>() and the C ABI')
+  parser.add_argument(
+      '--cuda-header', type=str, dest='cuda_header_file', metavar='file',
+      help='host C++ header declaring <app>() (same as --xocl-header)')
+  parser.add_argument(
+      '--cuda-temporal-depth', type=int, dest='cuda_depth', metavar='T',
+      help='iterations fused per kernel launch (default: chosen per program)')
+  parser.add_argument(
+      '--cuda-tile', type=int, nargs='+', dest='cuda_tile', metavar='N',
+      help='thread-block tile in the non-streamed dimensions')
+  parser.add_argument(
+      '--cuda-threads', type=int, dest='cuda_threads', metavar='N',
+      help='threads per block')
+  parser.add_argument(
+      '--cuda-vec', type=int, dest='cuda_vec', metavar='N',
+      help='cells per thread per vector access along dimension 0')
+  parser.add_argument(
+      '--cuda-prefetch', type=int, dest='cuda_prefetch', metavar='N',
+      help='input planes requested ahead by TMA')
+
+
+class Options:
+  """Tuning knobs of the backend; None means "choose for me"."""
+
+  def __init__(self, depth=None, tile=None, threads=None, vec=None,
+               prefetch=None):
+    self.depth, self.tile, self.threads = depth, tile, threads
+    self.vec, self.prefetch = vec, prefetch
+
+  @classmethod
+  def from_args(cls, args):
+    return cls(depth=getattr(args, 'cuda_depth', None),
+               tile=getattr(args, 'cuda_tile', None),
+               threads=getattr(args, 'cuda_threads', None),
+               vec=getattr(args, 'cuda_vec', None),
+               prefetch=getattr(args, 'cuda_prefetch', None))
+
+  def key(self):
+    return 'd%s_t%s_n%s_v%s_p%s' % (
+        self.depth, 'x'.join(map(str, self.tile)) if self.tile else None,
+        self.threads, self.vec, self.prefetch)
+
+
+def check_supported(program):
+  for name, haoda_type in list(program.types.items()):
+    if haoda_type not in SUPPORTED_TYPES:
+      raise util.SemanticError(
+          'type `%s` of `%s` is not supported by the CUDA backend' %
+          (haoda_type, name))
+  if program.params:
+    raise util.SemanticError('param statements are not supported by the CUDA '
+                             'backend yet')
+  if not 2 <= program.dim <= 4:
+    raise util.SemanticError('the CUDA backend handles 2- to 4-dimensional '
+                             'programs, not %d' % program.dim)
+  if len(program.inputs) > 8 or len(program.outputs) > 8:
+    raise util.SemanticError('at most 8 inputs and 8 outputs')
+
+
+def default_vec(program):
+  widest = max(util.get_width_in_bytes(t) for t in program.types.values())
+  return max(1, 16 // widest)
+
+
+def _default_tiles(program, vec):
+  """Candidate block tiles, preferred first."""
+  if program.dim == 2:
+    return [(128 * vec,), (64 * vec,), (32 * vec,)]
+  if program.dim == 3:
+    return [(16 * vec, 16), (16 * vec, 8), (8 * vec, 8)]
+  return [(8 * vec, 8, 4), (8 * vec, 4, 4)]
+
+
+def make_schedule(program, depth, options, limit=SMEM_LIMIT):
+  """The schedule for ``depth`` fused iterations: the caller's knobs where
+  given, otherwise the first candidate that fits in shared memory."""
+  vec = options.vec or default_vec(program)
+  tiles = [tuple(options.tile)] if options.tile else _default_tiles(program,
+                                                                    vec)
+  prefetches = ([options.prefetch] if options.prefetch is not None
+                else [3, 2, 1])
+  problem = None
+  for tile in tiles:
+    for prefetch in prefetches:
+      threads = options.threads or min(256, math.prod(tile) // vec)
+      try:
+        sched = plan_mod.Schedule(program, depth, tile, vec, threads, prefetch)
+        total = kernel_mod.Layout(sched).total
+      except util.SemanticError as e:
+        problem = problem or e
+        continue
+      if total <= limit:
+        return sched
+      problem = problem or util.SemanticError(
+          'depth %d with tile %s needs %d bytes of shared memory (limit %d)' %
+          (depth, tile, total, limit))
+  raise problem
+
+
+def make_schedules(program, options=None):
+  """The kernel variants to compile: the main temporal depth and, when it does
+  not divide ``iterate``, the depth of the remainder."""
+  options = options or Options()
+  check_supported(program)
+  iterate = program.iterate
+  if options.depth:
+    main = max(1, min(options.depth, iterate))
+  elif not program.feedback or iterate == 1:
+    main = 1
+  else:
+    main = 1
+    for depth in (2, 4, 8, 16):
+      if depth > iterate:
+        break
+      if program.dim > 2 and depth > 2:
+        break
+      try:
+        make_schedule(program, depth, options, SMEM_LIMIT // 2)
+      except util.SemanticError:
+        break
+      main = depth
+  depths = [main]
+  if iterate % main:
+    depths.append(iterate % main)
+  return [make_schedule(program, depth, options) for depth in depths]
+
+
+def print_kernel(program, schedules, kernel_file):
+  p = util.Printer(kernel_file)
+  p.println('// CUDA kernels of SODA program `%s` for sm_100a.' %
+            program.app_name)
+  p.println('// Generated by sodac --cuda-kernel; do not edit.')
+  p.println('// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false')
+  p.println('#include "soda_cuda_device.cuh"')
+  p.println('#include "soda_cuda_runtime.h"')
+  p.println()
+  layouts = [kernel_mod.emit_kernel(p, sched) for sched in schedules]
+  host_mod.emit_variant_table(p, program.app_name, schedules, layouts)
+
+
+def print_header(program, header_file):
+  """``<app>.h``: what reference header.print_code emits (header.py:7-64),
+  reduced to the buffer_t definition and the prototype."""
+  p = util.Printer(header_file)
+  guard = 'HALIDE_%s_H_' % program.app_name.upper()
+  names = [n for n, _ in program.inputs] + [n for n, _ in program.outputs]
+  p.printlns('#ifndef %s' % guard, '#define %s' % guard, '',
+             '#include "soda_cuda.h"  // buffer_t', '',
+             '#ifndef HALIDE_FUNCTION_ATTRS', '#define HALIDE_FUNCTION_ATTRS',
+             '#endif//HALIDE_FUNCTION_ATTRS', '')
+  p.println('int %s(%sconst char* xclbin) HALIDE_FUNCTION_ATTRS;' % (
+      program.app_name, ''.join('buffer_t *var_%s_buffer, ' % n
+                                for n in names)))
+  p.printlns('', '#endif//%s' % guard)
+
+
+def _emit(path, writer):
+  """Write through a temp file, then to ``path`` or stdout for ``-``
+  (same pattern as reference opencl.py:99-106)."""
+  with tempfile.TemporaryFile(mode='w+') as tmp:
+    writer(tmp)
+    tmp.seek(0)
+    if path == '-':
+      shutil.copyfileobj(tmp, sys.stdout)
+    else:
+      with open(path, 'w') as out:
+        shutil.copyfileobj(tmp, out)
+
+
+def print_code(stencil, args):
+  kernel_file = getattr(args, 'cuda_kernel_file', None)
+  host_file = getattr(args, 'cuda_host_file', None)
+  header_file = getattr(args, 'cuda_header_file', None)
+  if kernel_file is None and host_file is None and header_file is None:
+    return
+  program = plan_mod.extract_program(stencil)
+  check_supported(program)
+  if kernel_file is not None:
+    schedules = make_schedules(program, Options.from_args(args))
+    _emit(kernel_file, lambda f: print_kernel(program, schedules, f))
+  if host_file is not None:
+    _emit(host_file, lambda f: host_mod.print_code(program, f))
+  if header_file is not None:
+    _emit(header_file, lambda f: print_header(program, f))

@@ -1,0 +1,399 @@
+"""Scheduling of a SODA stencil onto the streaming GPU kernel.
+
+Two steps, both pure Python so they can be tested without a GPU:
+
+``extract_program(stencil)``
+    reads a ``soda.core.Stencil`` (this package's or, duck-typed, the
+    reference's) and keeps what execution needs: the stages of ONE iteration
+    in dependency order, each with its lowered expression and the relative
+    offsets of its loads (the ``ref.idx - st_ref.idx`` of the reference's
+    golden loop, src/soda/codegen/xilinx/host.py:1099-1101), plus how outputs
+    feed inputs across ``iterate`` (by position, src/soda/core.py:347-351).
+
+``Schedule(program, depth, tile, ...)``
+    maps ``depth`` fused iterations onto one kernel.  The model is the
+    reference's own dataflow pipeline turned sideways: the last dimension is
+    streamed (never tiled: src/soda/grammar.py:34, README.md:248), the others
+    are tiled.  A thread block owns one tile of the non-streamed dimensions and
+    walks the streamed dimension one *plane* (a row in 2-D, an x-y tile in 3-D)
+    per step.  Every tensor of the fused chain lives in a shared-memory ring
+    of planes — the GPU image of the reference's reuse buffers
+    (src/soda/core.py:612-777) — and every stage computes one plane per step,
+    ``delay`` steps behind the newest input plane, reading only planes that
+    were completed in earlier steps, so one block barrier per step suffices.
+
+Garbage tolerance.  All stages compute the whole tile; cells whose stencil
+reaches outside the tile (or outside the grid, where loads return 0) hold
+garbage.  Only cells whose whole transitive window lies inside the tile are
+stored, so tiles overlap by the accumulated halo, and in-plane neighbour
+addresses are plain linear offsets: a read that wraps into the next row or
+the next ring slot only ever feeds a garbage cell.  This removes every
+boundary branch from the stage bodies.
+"""
+import collections
+
+from haoda import util
+
+Load = collections.namedtuple('Load', 'parent off')   # off: offset per dim
+
+
+def _is_ref(obj):
+  return type(obj).__name__ == 'Ref'
+
+
+class Code:
+  """Leaf standing in for a Ref once an emitter has chosen its storage."""
+
+  def __init__(self, code):
+    self.c_expr = code
+
+  def __str__(self):
+    return self.c_expr
+
+  def visit(self, callback, args=None):
+    del callback, args
+    return self
+
+
+class Stage:
+  """One local/output statement of one iteration."""
+
+  def __init__(self, name, haoda_type, lets, expr, store_idx, is_output):
+    self.name = name
+    self.haoda_type = haoda_type
+    self.c_type = util.get_c_type(haoda_type)
+    self.lets = tuple(lets)   # ir.Let-like: .c_type .name .expr
+    self.expr = expr          # expression tree with Ref leaves
+    self.store_idx = tuple(store_idx)
+    self.is_output = is_output
+    self.loads = []           # unique Load, first-use order
+    for node in self.lets + (expr,):
+      node.visit(self._note_load)
+
+  def load_of(self, ref):
+    return Load(ref.name,
+                tuple(a - b for a, b in zip(ref.idx, self.store_idx)))
+
+  def _note_load(self, obj, _):
+    if _is_ref(obj):
+      load = self.load_of(obj)
+      if load not in self.loads:
+        self.loads.append(load)
+
+  def render(self, ref_code):
+    """``(let lines, expression)`` as C, each Ref replaced by ``ref_code(load)``.
+
+    The expression text is the IR's own ``c_expr`` lowering of the tree with
+    Refs swapped for storage accesses — the recipe of the golden loop's
+    ``mutate_load_for_host`` (host.py:1093-1117), so operator order and
+    parenthesisation are the reference's, quirks included.
+    """
+    def swap(obj, _):
+      if _is_ref(obj):
+        return Code(ref_code(self.load_of(obj)))
+      return obj
+    lets = ['const %s %s = %s;' % (let.c_type, let.name,
+                                   strip_parens(let.expr.visit(swap).c_expr))
+            for let in self.lets]
+    return lets, self.expr.visit(swap).c_expr
+
+
+def strip_parens(text):
+  # ``Let.c_expr`` unparenthesizes its right-hand side (ir Let.c_expr)
+  while text[:1] == '(' and text[-1:] == ')':
+    text = text[1:-1]
+  return text
+
+
+class Program:
+  """A stencil program reduced to what execution needs."""
+
+  def __init__(self, app_name, dim, iterate, inputs, outputs, stages,
+               params=()):
+    self.app_name = app_name
+    self.dim = dim
+    self.iterate = iterate
+    self.inputs = list(inputs)      # [(name, haoda_type)]
+    self.outputs = list(outputs)    # [(name, haoda_type)]
+    self.stages = list(stages)      # dependency order, one iteration
+    self.params = list(params)
+    self.input_names = [n for n, _ in self.inputs]
+    self.output_names = [n for n, _ in self.outputs]
+    self.types = dict(self.inputs)
+    self.types.update((s.name, s.haoda_type) for s in self.stages)
+    # output k of an iteration is input k of the next (by position)
+    self.feedback = (dict(zip(self.input_names, self.output_names))
+                     if len(self.inputs) == len(self.outputs) else {})
+
+  def c_type(self, name):
+    return util.get_c_type(self.types[name])
+
+  def elem_size(self, name):
+    return util.get_width_in_bytes(self.types[name])
+
+  def window(self, iterations=None):
+    """``(lo, hi)`` per dimension: bounding box of every offset at which the
+    outputs of ``iterations`` chained iterations read the original inputs —
+    the box of the reference's overall stencil window (core.py:793-830)."""
+    iterations = self.iterate if iterations is None else iterations
+    zero = (0,) * self.dim
+    reach = {name: (zero, zero) for name in self.input_names}
+    for it in range(iterations):
+      for stage in self.stages:
+        boxes = []
+        for load in stage.loads:
+          box = reach.get(load.parent)
+          if box is not None:   # params / input-free stages contribute nothing
+            boxes.append((tuple(map(sum, zip(box[0], load.off))),
+                          tuple(map(sum, zip(box[1], load.off)))))
+        reach[stage.name] = (
+            tuple(min(b[0][d] for b in boxes) for d in range(self.dim)),
+            tuple(max(b[1][d] for b in boxes) for d in range(self.dim))
+        ) if boxes else None
+      outs = [reach[name] for name in self.output_names if reach[name]]
+      if it + 1 < iterations:
+        reach = {name: reach[self.feedback[name]] for name in self.input_names}
+    if not outs:
+      return zero, zero
+    return (tuple(min(o[0][d] for o in outs) for d in range(self.dim)),
+            tuple(max(o[1][d] for o in outs) for d in range(self.dim)))
+
+  def valid_region(self, dims, iterations=None):
+    """``[(lo, hi)]`` per dimension where outputs are defined: the bounds of
+    the reference's golden loop (host.py:1082-1091)."""
+    lo, hi = self.window(iterations)
+    return [(max(0, -l), d - max(0, h)) for l, h, d in zip(lo, hi, dims)]
+
+
+def extract_program(stencil):
+  """soda.core.Stencil (ours or, duck-typed, the reference's) -> Program."""
+  n_in = len(stencil.input_stmts)
+  local_names = list(stencil.local_names)
+  output_names = list(stencil.output_names)
+  stage_names = local_names + output_names
+  # the first replica of every statement; with iterate > 1 the reference
+  # names an output of iteration 0 ``<input>_iter1`` — undo that by position
+  replicas = list(stencil.tensors.values())[n_in:n_in + len(stage_names)]
+  by_name = {
+      name: Stage(name, tensor.haoda_type, tensor.lets, tensor.expr,
+                  tensor.st_ref.idx, name in output_names)
+      for name, tensor in zip(stage_names, replicas)}
+  known = set(stencil.input_names) | set(stencil.param_names)
+  placed, order, pending = set(known), [], list(stage_names)
+  while pending:
+    ready = [name for name in pending
+             if {load.parent for load in by_name[name].loads} <= placed]
+    if not ready:
+      bad = {load.parent for name in pending for load in by_name[name].loads}
+      bad -= placed | set(stage_names)
+      raise util.SemanticError(
+          'unknown tensor(s) %s' % ', '.join(sorted(bad)) if bad else
+          'cyclic dependency among %s' % ', '.join(pending))
+    for name in ready:
+      placed.add(name)
+      order.append(by_name[name])
+      pending.remove(name)
+  return Program(
+      stencil.app_name, stencil.dim, stencil.iterate,
+      list(zip(stencil.input_names, stencil.input_types)),
+      list(zip(stencil.output_names, stencil.output_types)),
+      order, params=list(stencil.param_names))
+
+
+# --- the fused, streamed schedule --------------------------------------------
+
+def _pow2(n):
+  p = 1
+  while p < n:
+    p *= 2
+  return p
+
+
+class Node:
+  """A tensor of the fused chain: an input plane stream or a stage replica."""
+
+  def __init__(self, index, name, iteration, stage, c_type, elem_size):
+    self.index = index
+    self.name = name            # program tensor name
+    self.iteration = iteration  # fused iteration it belongs to (inputs: -1)
+    self.stage = stage          # None for inputs
+    self.c_type = c_type
+    self.elem_size = elem_size
+    self.loads = []             # [(Node, off)] resolved, stage.loads order
+    self.consumers = []         # [(Node, off)]
+    self.delay = 0              # computes/receives plane (b - delay) at step b
+    self.ring_depth = 0         # planes in shared memory (0: no ring)
+    self.output_index = None    # position among program outputs if stored
+    self.input_index = None
+
+  @property
+  def is_input(self):
+    return self.stage is None
+
+  @property
+  def ident(self):
+    return self.name if self.iteration <= 0 else '%s_t%d' % (self.name,
+                                                             self.iteration)
+
+  @property
+  def avail(self):
+    """At step b the newest plane of this tensor a stage may read is b-avail."""
+    return self.delay if self.is_input else self.delay + 1
+
+
+class Schedule:
+  """``depth`` iterations of ``program`` fused into one streaming kernel.
+
+  Args:
+    depth: iterations fused per launch (temporal blocking depth T).
+    tile: extents of the block tile in the non-streamed dims, dim 0 first.
+    vec: cells per thread per vector along dim 0.
+    threads: threads per block.
+    prefetch: input planes requested ahead of the one being consumed.
+  """
+
+  def __init__(self, program, depth, tile, vec, threads, prefetch=2):
+    self.program = program
+    self.depth = depth
+    self.tile = tuple(tile)
+    self.vec = vec
+    self.threads = threads
+    self.prefetch = prefetch
+    dim = program.dim
+    if dim < 2:
+      raise util.SemanticError(
+          'the streaming kernel needs at least one tiled dimension')
+    if len(self.tile) != dim - 1:
+      raise util.SemanticError('tile must have %d extents' % (dim - 1))
+    if depth > 1 and not program.feedback:
+      raise util.SemanticError(
+          'cannot fuse iterations: outputs do not pair with inputs')
+    self.sdim = dim - 1                      # streamed dimension
+    self.plane_elems = 1
+    for extent in self.tile:
+      self.plane_elems *= extent
+    if self.tile[0] % vec:
+      raise util.SemanticError('tile width must be a multiple of vec')
+    self.plane_vecs = self.plane_elems // vec
+    if self.plane_vecs % threads:
+      raise util.SemanticError('threads must divide the vectors per plane')
+    self.vecs_per_thread = self.plane_vecs // threads
+    self._build_nodes()
+    self._assign_delays()
+    self._size_rings()
+    self._measure_halos()
+
+  # pitch of each tiled dim in elements within a plane
+  def plane_pitch(self, d):
+    pitch = 1
+    for extent in self.tile[:d]:
+      pitch *= extent
+    return pitch
+
+  def plane_offset(self, off):
+    """Linear in-plane offset of a load (tiled dims only)."""
+    return sum(off[d] * self.plane_pitch(d) for d in range(self.sdim))
+
+  def _build_nodes(self):
+    program = self.program
+    self.nodes = []
+    current = {}       # program tensor name -> Node visible to this iteration
+    for k, (name, haoda_type) in enumerate(program.inputs):
+      node = Node(len(self.nodes), name, -1, None, util.get_c_type(haoda_type),
+                  util.get_width_in_bytes(haoda_type))
+      node.input_index = k
+      self.nodes.append(node)
+      current[name] = node
+    self.inputs = list(self.nodes)
+    self.stage_nodes = []
+    for it in range(self.depth):
+      for stage in program.stages:
+        node = Node(len(self.nodes), stage.name, it, stage, stage.c_type,
+                    util.get_width_in_bytes(stage.haoda_type))
+        for load in stage.loads:
+          if load.parent in program.params:
+            continue
+          parent = current[load.parent]
+          node.loads.append((parent, load.off))
+          parent.consumers.append((node, load.off))
+        self.nodes.append(node)
+        self.stage_nodes.append(node)
+        current[stage.name] = node
+      if it + 1 < self.depth:
+        for name in program.input_names:
+          current[name] = current[program.feedback[name]]
+    self.outputs = []
+    for k, name in enumerate(program.output_names):
+      current[name].output_index = k
+      self.outputs.append(current[name])
+
+  def _assign_delays(self):
+    s = self.sdim
+    for node in self.stage_nodes:
+      needs = [parent.avail + off[s] for parent, off in node.loads]
+      node.delay = max(needs) if needs else 0
+    self.out_delay = max(node.delay for node in self.outputs)
+
+  def _size_rings(self):
+    s = self.sdim
+    for node in self.nodes:
+      if not node.consumers:
+        node.ring_depth = 0
+        continue
+      # oldest plane any consumer still reads at step b is b - oldest
+      oldest = max(c.delay - off[s] for c, off in node.consumers)
+      if node.is_input:
+        span = oldest + self.prefetch + 1
+      else:
+        span = oldest - node.delay + 1
+      node.ring_depth = _pow2(max(span, 1))
+
+  def _measure_halos(self):
+    lo, hi = self.program.window(self.depth)
+    self.window = (lo, hi)
+    self.halo_lo = [max(0, -l) for l in lo]
+    self.halo_hi = [max(0, h) for h in hi]
+    # dim 0 halos round up to whole vectors so owned cells stay vector aligned
+    v = self.vec
+    self.tile_halo_lo = [(-(-self.halo_lo[0] // v)) * v] + self.halo_lo[1:-1]
+    self.tile_halo_hi = [(-(-self.halo_hi[0] // v)) * v] + self.halo_hi[1:-1]
+    self.own = [t - a - b for t, a, b in
+                zip(self.tile, self.tile_halo_lo, self.tile_halo_hi)]
+    if min(self.own) <= 0:
+      raise util.SemanticError(
+          'tile %s is not larger than the halo of %d fused iteration(s)' %
+          (self.tile, self.depth))
+    # steps before/after the owned streamed range [r0, r1):
+    # b runs from r0 - lead to r1 - 1 + out_delay
+    self.lead = self.halo_lo[self.sdim]
+    # any single load's in-plane reach, for the guard zones around the rings
+    reach = [abs(self.plane_offset(off)) for node in self.stage_nodes
+             for _, off in node.loads]
+    self.guard_elems = max(reach) if reach else 0
+
+  def steps(self, rows):
+    """Steps a block runs to produce ``rows`` owned streamed planes."""
+    return rows + self.lead + self.out_delay
+
+  def smem_bytes(self):
+    total = 0
+    for node in self.nodes:
+      ring = node.ring_depth * self.plane_elems * node.elem_size
+      total += -(-ring // 128) * 128
+    guard = -(-self.guard_elems * 8 // 128) * 128
+    barriers = 8 * max([n.ring_depth for n in self.inputs] + [1]) * \
+        len(self.inputs)
+    return total + 2 * guard + -(-barriers // 128) * 128
+
+  def describe(self):
+    lines = ['schedule %s: depth %d, tile %s, vec %d, %d threads, own %s, '
+             'halo -%s +%s, lead %d, out delay %d, smem %d B' % (
+                 self.program.app_name, self.depth, self.tile, self.vec,
+                 self.threads, self.own, self.tile_halo_lo, self.tile_halo_hi,
+                 self.lead, self.out_delay, self.smem_bytes())]
+    for node in self.nodes:
+      lines.append('  %-16s delay %3d ring %2d %s' % (
+          node.ident, node.delay, node.ring_depth,
+          '-> out[%d]' % node.output_index
+          if node.output_index is not None else ''))
+    return '\n'.join(lines)

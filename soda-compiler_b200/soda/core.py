@@ -164,6 +164,32 @@ class Stencil:
             (stmt.name, len(stmt.ref.idx), self.dim))
     self.tensors    # builds and checks the DAG  pylint: disable=pointless-statement
 
+  @classmethod
+  def from_text(cls, text, iterate=None, burst_width=None, unroll_factor=None,
+                tile_size=None, dram_in=None, dram_out=None):
+    """Parse SODA source and build the Stencil with sodac's overrides applied
+    (what reference src/sodac:80-123 does between reading the file and
+    calling the backend).  ``tile_size``: per-dimension, 0 = keep."""
+    model = grammar.parse(text)
+    tiles = []
+    for d in range(model.dim - 1):
+      forced = tile_size[d] if tile_size and d < len(tile_size) else 0
+      tiles.append(forced if forced > 0 else model.tile_size[d])
+    tiles.append(0)
+    pick = lambda given, parsed: parsed if given is None else given
+    return cls(burst_width=pick(burst_width, model.burst_width),
+               iterate=pick(iterate, model.iterate), dram_in=dram_in,
+               dram_out=dram_out, app_name=model.app_name,
+               input_stmts=model.input_stmts, param_stmts=model.param_stmts,
+               local_stmts=model.local_stmts, output_stmts=model.output_stmts,
+               dim=model.dim, tile_size=tiles,
+               unroll_factor=pick(unroll_factor, model.unroll_factor))
+
+  @classmethod
+  def from_file(cls, path, **overrides):
+    with open(path) as handle:
+      return cls.from_text(handle.read(), **overrides)
+
   @staticmethod
   def _apply_dram(kind, stmts, spec, separator):
     """``name:1.2<sep>name2:3`` or ``1.2`` for all (reference :198-226)."""

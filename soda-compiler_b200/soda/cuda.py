@@ -1,0 +1,348 @@
+"""Build, load and run SODA programs on a B200: ``soda.cuda.run(stencil, arrays)``.
+
+The thin Python side of the CUDA backend: it drives ``soda.codegen.cuda`` to emit
+the kernel and host files of a ``soda.core.Stencil``, compiles them offline with
+``nvcc -gencode arch=compute_100a,code=sm_100a`` into one shared library per
+program, and calls that library through the C ABI of include/soda_cuda.h with
+ctypes.  There is no CPU fallback and no other backend: without nvcc the build
+raises, without a CUDA device the library returns ``no_device_interface``
+(-19) and ``run`` raises.
+
+Arrays follow the reference harness' layout (reference
+src/soda/codegen/xilinx/host.py:1011-1020): dense, dimension 0 fastest — a numpy
+array of shape ``(dims[n-1], ..., dims[0])``, C-contiguous.  numpy arrays are
+host buffers (copied to and from the device inside the call); torch CUDA
+tensors are passed zero-copy through ``buffer_t.dev``.
+"""
+import ctypes
+import hashlib
+import io
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+from haoda import util
+from soda.codegen import cuda as codegen
+from soda.codegen.cuda import host as host_gen
+from soda.codegen.cuda import plan as plan_mod
+
+_PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC_DIR = os.path.join(_PKG_ROOT, 'csrc')
+INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_ROOT), 'include')
+DEFAULT_BUILD_DIR = os.path.join(_PKG_ROOT, '_build')
+ARCH_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+NUMPY_TYPES = {
+    'uint8': np.uint8, 'uint16': np.uint16, 'uint32': np.uint32,
+    'uint64': np.uint64, 'int8': np.int8, 'int16': np.int16,
+    'int32': np.int32, 'int64': np.int64, 'float': np.float32,
+    'float32': np.float32, 'double': np.float64, 'float64': np.float64}
+
+ERROR_NAMES = {
+    -1: 'generic_error', -3: 'bad_elem_size', -4: 'access_out_of_bounds',
+    -6: 'buffer_extents_too_large', -11: 'out_of_memory',
+    -12: 'buffer_argument_is_null', -14: 'copy_to_host_failed',
+    -15: 'copy_to_device_failed', -16: 'device_malloc_failed',
+    -17: 'device_sync_failed', -19: 'no_device_interface',
+    -22: 'internal_error', -23: 'device_run_failed'}
+
+
+class CudaError(RuntimeError):
+  """A call into a compiled SODA library failed (code: Halide numbering)."""
+
+  def __init__(self, what, code):
+    super().__init__('%s failed: %d (%s)' % (
+        what, code, ERROR_NAMES.get(code, 'unknown')))
+    self.code = code
+
+
+class BufferT(ctypes.Structure):
+  """Legacy Halide buffer_t (reference header.py:36-48); sizeof == 72."""
+  _fields_ = [('dev', ctypes.c_uint64), ('host', ctypes.c_void_p),
+              ('extent', ctypes.c_int32 * 4), ('stride', ctypes.c_int32 * 4),
+              ('min', ctypes.c_int32 * 4), ('elem_size', ctypes.c_int32),
+              ('host_dirty', ctypes.c_bool), ('dev_dirty', ctypes.c_bool),
+              ('_padding', ctypes.c_uint8 * 2)]
+
+
+class Stats(ctypes.Structure):
+  _fields_ = [('kernel_ms', ctypes.c_double), ('h2d_ms', ctypes.c_double),
+              ('d2h_ms', ctypes.c_double), ('cells', ctypes.c_int64),
+              ('iterate', ctypes.c_int32), ('launches', ctypes.c_int32),
+              ('depth', ctypes.c_int32), ('used_tma', ctypes.c_int32),
+              ('blocks', ctypes.c_int32), ('threads', ctypes.c_int32),
+              ('smem_bytes', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+
+  def as_dict(self):
+    return {name: getattr(self, name) for name, _ in self._fields_
+            if name != 'reserved'}
+
+
+# --- build --------------------------------------------------------------------
+
+def generate_sources(stencil, options=None):
+  """``(program, kernel source, host source)`` for a Stencil."""
+  program = plan_mod.extract_program(stencil)
+  schedules = codegen.make_schedules(program, options)
+  kernel, host = io.StringIO(), io.StringIO()
+  codegen.print_kernel(program, schedules, kernel)
+  host_gen.print_code(program, host)
+  return program, kernel.getvalue(), host.getvalue()
+
+
+def nvcc_command(sources, output, fast_math=False, extra=()):
+  flags = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC', '-shared',
+           '-I', CSRC_DIR, '-I', INCLUDE_DIR]
+  # exact mode: no FMA contraction, so float results match the reference's
+  # x86-64 golden loop bit for bit
+  flags += ['-DSODA_CUDA_FAST_MATH'] if fast_math else ['-fmad=false']
+  return (['nvcc'] + ARCH_FLAGS + flags + list(extra) + list(sources) +
+          ['-o', output])
+
+
+def build(stencil, build_dir=None, options=None, fast_math=False,
+          force=False, verbose=False):
+  """Emit and compile ``stencil``; returns the path of ``libsoda_<app>.so``.
+
+  Builds are cached by a hash of the generated and hand-written sources and
+  the flags, under ``<package>/_build/<app>-<hash>/`` (in-tree on purpose: the
+  libraries travel with the repository snapshot to GPU machines).
+  """
+  if shutil.which('nvcc') is None:
+    raise RuntimeError('nvcc not found: the SODA CUDA backend compiles its '
+                       'kernels offline and has no other execution path')
+  program, kernel_src, host_src = generate_sources(stencil, options)
+  runtime = os.path.join(CSRC_DIR, 'soda_cuda_runtime.cu')
+  digest = hashlib.sha256()
+  for text in (kernel_src, host_src, str(fast_math)):
+    digest.update(text.encode())
+  for name in sorted(os.listdir(CSRC_DIR)) + ['../../include/soda_cuda.h']:
+    with open(os.path.join(CSRC_DIR, name), 'rb') as handle:
+      digest.update(handle.read())
+  out_dir = os.path.join(build_dir or DEFAULT_BUILD_DIR, '%s-%s' % (
+      program.app_name, digest.hexdigest()[:12]))
+  lib = os.path.join(out_dir, 'libsoda_%s.so' % program.app_name)
+  if os.path.exists(lib) and not force:
+    return lib
+  os.makedirs(out_dir, exist_ok=True)
+  kernel_path = os.path.join(out_dir, '%s_kernel.cu' % program.app_name)
+  host_path = os.path.join(out_dir, '%s_host.cpp' % program.app_name)
+  with open(kernel_path, 'w') as handle:
+    handle.write(kernel_src)
+  with open(host_path, 'w') as handle:
+    handle.write(host_src)
+  command = nvcc_command([kernel_path, host_path, runtime], lib + '.tmp',
+                         fast_math, ['-Xptxas', '-v'] if verbose else [])
+  done = subprocess.run(command, stdout=subprocess.PIPE,
+                        stderr=subprocess.STDOUT, text=True, check=False)
+  if verbose:
+    print(done.stdout)
+  if done.returncode != 0:
+    raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (
+        program.app_name, ' '.join(command), done.stdout))
+  os.replace(lib + '.tmp', lib)
+  return lib
+
+
+# --- load ---------------------------------------------------------------------
+
+class Library:
+  """A compiled SODA program, bound through the C ABI (include/soda_cuda.h)."""
+
+  def __init__(self, path):
+    self.path = path
+    lib = self._lib = ctypes.CDLL(path)
+    c_int, c_void_p, c_char_p = ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    bufpp = ctypes.POINTER(ctypes.POINTER(BufferT))
+    voidpp = ctypes.POINTER(c_void_p)
+    for name, restype, argtypes in (
+        ('soda_cuda_app_name', c_char_p, []),
+        ('soda_cuda_dim', c_int, []),
+        ('soda_cuda_iterate', c_int, []),
+        ('soda_cuda_num_inputs', c_int, []),
+        ('soda_cuda_num_outputs', c_int, []),
+        ('soda_cuda_tensor_name', c_char_p, [c_int, c_int]),
+        ('soda_cuda_tensor_type', c_char_p, [c_int, c_int]),
+        ('soda_cuda_tensor_elem_size', c_int, [c_int, c_int]),
+        ('soda_cuda_window', c_int, [c_int, i32p, i32p]),
+        ('soda_cuda_run', c_int, [bufpp, bufpp, c_char_p]),
+        ('soda_cuda_run_device', c_int,
+         [voidpp, voidpp, i32p, c_int, c_void_p]),
+        ('soda_cuda_launch', c_int,
+         [c_int, voidpp, voidpp, i32p, c_int, c_int, i32p, i32p, c_void_p]),
+        ('soda_cuda_depths', c_int, [i32p, c_int]),
+        ('soda_cuda_last_stats', ctypes.POINTER(Stats), []),
+        ('soda_cuda_release', None, []),
+    ):
+      fn = getattr(lib, name)
+      fn.restype, fn.argtypes = restype, argtypes
+    self.app_name = lib.soda_cuda_app_name().decode()
+    self.dim = lib.soda_cuda_dim()
+    self.iterate = lib.soda_cuda_iterate()
+    self.inputs = [(lib.soda_cuda_tensor_name(0, k).decode(),
+                    lib.soda_cuda_tensor_type(0, k).decode())
+                   for k in range(lib.soda_cuda_num_inputs())]
+    self.outputs = [(lib.soda_cuda_tensor_name(1, k).decode(),
+                     lib.soda_cuda_tensor_type(1, k).decode())
+                    for k in range(lib.soda_cuda_num_outputs())]
+    depths = (ctypes.c_int32 * 16)()
+    self.depths = list(depths[:lib.soda_cuda_depths(depths, 16)])
+
+  def window(self, iterate=None):
+    """``(lo, hi)`` offsets per dim read by an output cell after ``iterate``."""
+    lo, hi = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 4)()
+    code = self._lib.soda_cuda_window(
+        self.iterate if iterate is None else iterate, lo, hi)
+    if code:
+      raise CudaError('soda_cuda_window', code)
+    return tuple(lo[:self.dim]), tuple(hi[:self.dim])
+
+  def valid_region(self, dims, iterate=None):
+    lo, hi = self.window(iterate)
+    return [(max(0, -l), n - max(0, h)) for l, h, n in zip(lo, hi, dims)]
+
+  @property
+  def stats(self):
+    return self._lib.soda_cuda_last_stats().contents.as_dict()
+
+  def release(self):
+    self._lib.soda_cuda_release()
+
+  # ---- buffers ----
+  def _describe(self, array, haoda_type, what):
+    """array -> (BufferT, dims); numpy = host memory, torch CUDA = device."""
+    elem = util.get_width_in_bytes(haoda_type)
+    buf = BufferT()
+    if isinstance(array, np.ndarray):
+      if array.dtype != NUMPY_TYPES[haoda_type]:
+        raise TypeError('%s must be %s, got %s' % (what, haoda_type,
+                                                   array.dtype))
+      if not array.flags['C_CONTIGUOUS']:
+        raise ValueError('%s must be C-contiguous' % what)
+      buf.host = array.ctypes.data
+      shape = array.shape
+    elif hasattr(array, 'data_ptr'):    # torch tensor
+      if not array.is_contiguous():
+        raise ValueError('%s must be contiguous' % what)
+      if array.element_size() != elem:
+        raise TypeError('%s must have %d-byte elements' % (what, elem))
+      if array.is_cuda:
+        buf.dev = array.data_ptr()
+      else:
+        buf.host = array.data_ptr()
+      shape = tuple(array.shape)
+    else:
+      raise TypeError('%s: expected a numpy array or a torch tensor' % what)
+    if len(shape) != self.dim:
+      raise ValueError('%s must be %d-dimensional' % (what, self.dim))
+    dims = tuple(reversed(shape))
+    stride = 1
+    for d, extent in enumerate(dims):
+      buf.extent[d], buf.stride[d] = extent, stride
+      stride *= extent
+    buf.elem_size = elem
+    return buf, dims
+
+  def run(self, inputs, outputs=None):
+    """Run the whole program (all ``iterate`` iterations); returns outputs.
+
+    ``inputs`` in program order.  ``outputs``: arrays to fill, or None to
+    allocate them like the first input (numpy -> numpy, torch -> torch).
+    """
+    if len(inputs) != len(self.inputs):
+      raise ValueError('%s takes %d input(s)' % (self.app_name,
+                                                 len(self.inputs)))
+    in_bufs = []
+    dims = None
+    for array, (name, haoda_type) in zip(inputs, self.inputs):
+      buf, got = self._describe(array, haoda_type, 'input `%s`' % name)
+      if dims is not None and got != dims:
+        raise ValueError('input `%s` has extent %s, expected %s' %
+                         (name, got, dims))
+      dims = got
+      in_bufs.append(buf)
+    if outputs is None:
+      outputs = [self._allocate_like(inputs[0], haoda_type, dims)
+                 for _, haoda_type in self.outputs]
+    out_bufs = []
+    for array, (name, haoda_type) in zip(outputs, self.outputs):
+      buf, got = self._describe(array, haoda_type, 'output `%s`' % name)
+      if got != dims:
+        raise ValueError('output `%s` has extent %s, expected %s' %
+                         (name, got, dims))
+      out_bufs.append(buf)
+    in_ptrs = (ctypes.POINTER(BufferT) * len(in_bufs))(
+        *[ctypes.pointer(b) for b in in_bufs])
+    out_ptrs = (ctypes.POINTER(BufferT) * len(out_bufs))(
+        *[ctypes.pointer(b) for b in out_bufs])
+    code = self._lib.soda_cuda_run(in_ptrs, out_ptrs, None)
+    if code:
+      raise CudaError('soda_cuda_run(%s)' % self.app_name, code)
+    return list(outputs)
+
+  @staticmethod
+  def _allocate_like(like, haoda_type, dims):
+    shape = tuple(reversed(dims))
+    if isinstance(like, np.ndarray):
+      return np.empty(shape, dtype=NUMPY_TYPES[haoda_type])
+    import torch
+    dtype = torch.from_numpy(np.empty(0, NUMPY_TYPES[haoda_type])).dtype
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+  # ---- device-resident entry points (torch CUDA tensors or raw pointers) ----
+  @staticmethod
+  def _pointers(items):
+    values = [item.data_ptr() if hasattr(item, 'data_ptr') else int(item)
+              for item in items]
+    return (ctypes.c_void_p * len(values))(*values)
+
+  def run_device(self, inputs, outputs, dims, iterate=0, stream=None):
+    """Enqueue all iterations on device arrays (asynchronous)."""
+    code = self._lib.soda_cuda_run_device(
+        self._pointers(inputs), self._pointers(outputs),
+        (ctypes.c_int32 * 4)(*dims), iterate, stream)
+    if code:
+      raise CudaError('soda_cuda_run_device(%s)' % self.app_name, code)
+
+  def launch(self, depth, inputs, outputs, dims, row_begin, row_end,
+             valid_lo, valid_hi, stream=None):
+    """Enqueue one kernel launch (see soda_cuda_launch)."""
+    pad = lambda xs, fill: (ctypes.c_int32 * 4)(
+        *(list(xs) + [fill] * (4 - len(xs))))
+    code = self._lib.soda_cuda_launch(
+        depth, self._pointers(inputs), self._pointers(outputs), pad(dims, 1),
+        row_begin, row_end, pad(valid_lo, 0), pad(valid_hi, 1), stream)
+    if code:
+      raise CudaError('soda_cuda_launch(%s)' % self.app_name, code)
+
+
+_loaded = {}
+
+
+def load(path):
+  path = os.path.abspath(path)
+  if path not in _loaded:
+    _loaded[path] = Library(path)
+  return _loaded[path]
+
+
+def compile_stencil(stencil, **kwargs):
+  """Build (cached) and load the library of ``stencil``."""
+  return load(build(stencil, **kwargs))
+
+
+def run(stencil, arrays, **kwargs):
+  """Run ``stencil`` on ``arrays`` on the current CUDA device.
+
+  ``arrays``: the inputs in program order, or a dict by input name.  Returns
+  the outputs in program order (a dict by name if ``arrays`` was a dict).
+  """
+  library = compile_stencil(stencil, **kwargs)
+  if isinstance(arrays, dict):
+    inputs = [arrays[name] for name, _ in library.inputs]
+    outputs = library.run(inputs)
+    return {name: out for (name, _), out in zip(library.outputs, outputs)}
+  return library.run(list(arrays))

@@ -1,0 +1,129 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI (needs a GPU).
+
+Bar (BASELINE.json north_star): bit-exact for integer stencils and — in the
+default exact build (-fmad=false, reference operation order, double sqrt) —
+for float stencils too.  Every comparison below is bitwise over the WHOLE
+array: the valid region must match the oracle and the border must be 0.
+"""
+import numpy as np
+import pytest
+
+import common
+from soda import cuda as soda_cuda
+from soda.codegen import cuda as codegen
+
+pytestmark = pytest.mark.gpu
+
+# name, iterate, dims, backend options
+CASES = [
+    # BASELINE config 1, the reference's own CPU-runnable case
+    ('blur', 1, (2000, 1000), {}),
+    # one per benchmark, dims not multiples of anything (plain-load path,
+    # scalar stores, partial tiles, several tiles and chunks)
+    ('blur', 1, (1037, 211), {}),
+    ('sobel2d', 1, (1101, 157), {}),
+    ('jacobi2d', 1, (1203, 95), {}),
+    ('seidel2d', 2, (999, 130), {}),
+    ('denoise2d', 1, (777, 141), {}),
+    ('jacobi3d', 2, (101, 67, 45), {}),
+    ('heat3d', 2, (131, 35, 52), {}),
+    ('denoise3d', 1, (93, 41, 37), {}),
+    # aligned dims: TMA path + 128-bit stores
+    ('sobel2d', 1, (2048, 96), {}),
+    ('jacobi2d', 2, (1536, 200), {}),
+    ('jacobi2d', 7, (1024, 300), {'depth': 4}),      # 4 + 3 remainder
+    ('jacobi2d', 16, (2048, 260), {'depth': 8}),
+    ('seidel2d', 4, (1280, 160), {'depth': 2}),
+    ('denoise2d', 1, (1024, 128), {}),
+    ('jacobi3d', 4, (128, 64, 40), {'depth': 2}),
+    ('heat3d', 3, (192, 48, 33), {'depth': 2}),      # 2 + 1 remainder
+    ('heat3d', 1, (256, 128, 64), {}),
+    ('denoise3d', 1, (128, 48, 24), {}),
+]
+
+
+def _library(name, iterate, options):
+  return soda_cuda.compile_stencil(common.stencil(name, iterate),
+                                   options=codegen.Options(**options))
+
+
+def _ids(case):
+  name, iterate, dims, options = case
+  return '%s-it%d-%s%s' % (name, iterate, 'x'.join(map(str, dims)),
+                           ''.join('-%s%s' % kv for kv in options.items()))
+
+
+@pytest.mark.parametrize('case', CASES, ids=_ids)
+def test_matches_oracle_on_reference_inputs(case):
+  name, iterate, dims, options = case
+  orc = common.oracle(name, iterate)
+  inputs = orc.reference_inputs(dims)
+  want = orc.run(inputs)
+  got = _library(name, iterate, options).run(inputs)
+  for k, (g, w) in enumerate(zip(got, want)):
+    common.assert_bit_exact(g, w, '%s output %d' % (_ids(case), k))
+
+
+@pytest.mark.parametrize('case', CASES[1:], ids=_ids)
+def test_matches_oracle_on_random_inputs(case):
+  name, iterate, dims, options = case
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=len(name) + iterate)
+  want = orc.run(inputs)
+  got = _library(name, iterate, options).run(inputs)
+  for k, (g, w) in enumerate(zip(got, want)):
+    common.assert_bit_exact(g, w, '%s output %d' % (_ids(case), k))
+
+
+@pytest.mark.parametrize('name,iterate,dims', [
+    ('jacobi2d', 2, (1536, 200)), ('heat3d', 1, (256, 128, 64)),
+    ('sobel2d', 1, (2048, 96))])
+def test_plain_load_path_equals_tma_path(name, iterate, dims, monkeypatch):
+  """Same aligned problem through both input paths gives identical bits."""
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=7)
+  library = _library(name, iterate, {})
+  with_tma = library.run(inputs)
+  assert library.stats['used_tma'] == 1
+  monkeypatch.setenv('SODA_CUDA_NO_TMA', '1')
+  without = library.run(inputs)
+  assert library.stats['used_tma'] == 0
+  for a, b in zip(with_tma, without):
+    common.assert_bit_exact(a, b, name)
+
+
+def test_device_buffers_zero_copy():
+  """torch CUDA tensors go through buffer_t.dev without host copies."""
+  import torch
+  name, iterate, dims = 'jacobi2d', 3, (1024, 128)
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=3)
+  want = orc.run(inputs)
+  library = _library(name, iterate, {})
+  dev_in = [torch.from_numpy(a).cuda() for a in inputs]
+  keep = [t.clone() for t in dev_in]
+  dev_out = library.run(dev_in)
+  torch.cuda.synchronize()
+  assert library.stats['h2d_ms'] == 0 or library.stats['h2d_ms'] < 1.0
+  common.assert_bit_exact(dev_out[0].cpu().numpy(), want[0], 'device run')
+  assert torch.equal(dev_in[0], keep[0]), 'inputs must not be modified'
+
+
+def test_chunking_does_not_change_results(monkeypatch):
+  """Any split of the streamed dimension gives the same bits."""
+  name, iterate, dims = 'seidel2d', 2, (640, 333)
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=11)
+  want = orc.run(inputs)
+  library = _library(name, iterate, {})
+  for chunks in ('1', '2', '7', '333'):
+    monkeypatch.setenv('SODA_CUDA_CHUNKS', chunks)
+    got = library.run(inputs)
+    common.assert_bit_exact(got[0], want[0], 'chunks=' + chunks)
+
+
+def test_bad_elem_size_is_rejected():
+  library = _library('jacobi2d', 2, {})
+  wrong = [np.zeros((64, 64), dtype=np.float64)]
+  with pytest.raises(TypeError):
+    library.run(wrong)
