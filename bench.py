@@ -1,0 +1,327 @@
+#!/usr/bin/env python3
+"""Headline benchmark: GCell/s of a SODA stencil program on B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): jacobi2d, float32, 16384 x 16384,
+iterate 64.  One "step" is one complete run of the program: 64 iterations
+over the whole grid = 1.718e10 cell updates.  With N > 1 GPUs (launched by
+torch.distributed.run, one process per GPU) every rank owns a 16384-row slab
+of a 16384 x (16384 N) grid and exchanges halo rows over NCCL after every
+temporally blocked launch: weak scaling, value = all ranks' cell updates / s.
+
+What is timed
+  value     inputs resident in HBM, CUDA events around K steps on the launch
+            stream, max over ranks.
+  e2e       the same K steps through the reference-facing C ABI entry
+            (soda_cuda_run, the generic form of `<app>(buffer_t*...)`) with
+            pinned HOST buffers: H2D of the input and D2H of the output are
+            inside the timed region.
+  roofline  the streaming kernel: algorithmic bytes per launch (8 B x cells:
+            each input cell read once, each output cell written once;
+            SURVEY.md 8d) / mean launch time, against the measured HBM copy
+            bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle (a port of the reference's golden loop, built
+            with the pinned flags) on the host's cores, on a bounded sample.
+
+--impl reference times that CPU port alone with all host threads (the
+reference has no executable of its own for this path: SURVEY.md 0.1).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [os.path.join(ROOT, 'soda-compiler_b200')]
+
+WORKLOAD = dict(program='jacobi2d', iterate=64, dims=(16384, 16384))
+BYTES_PER_CELL = 8          # float32 in + float32 out
+CPU_SAMPLE_ITERATE = 4      # iterations of the same grid timed on the CPU
+HBM_FALLBACK_GBS = 6650.0   # B200_PROFILING.md, if MEASURED_PEAKS.json absent
+
+
+def measured_hbm_gbs():
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as handle:
+      return float(json.load(handle)['hbm_gbs']), 'measured'
+  except (OSError, KeyError, ValueError):
+    return HBM_FALLBACK_GBS, 'fallback'
+
+
+def load_stencil(iterate=None):
+  from soda import core
+  path = os.path.join(ROOT, 'benchmarks', WORKLOAD['program'] + '.soda')
+  return core.Stencil.from_file(
+      path, iterate=WORKLOAD['iterate'] if iterate is None else iterate)
+
+
+class ClockSampler:
+  """nvidia-smi clocks and throttle reasons while the timed region runs."""
+  QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,'
+           'clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.rows = []
+    self._proc = None
+    try:
+      self._proc = subprocess.Popen(
+          ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+           '--format=csv,noheader,nounits', '-lms', '100'],
+          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self._thread = threading.Thread(target=self._read, daemon=True)
+      self._thread.start()
+    except OSError:
+      self._proc = None
+
+  def _read(self):
+    for line in self._proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self._proc is None:
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
+    self._proc.terminate()
+    self._thread.join(timeout=2)
+    clocks = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    reasons = set()
+    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+             'sw_power_cap')
+    for row in self.rows:
+      for name, cell in zip(names, row[2:6]):
+        if cell.lower().startswith('active'):
+          reasons.add(name)
+    top = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    return {'sm_mhz': clocks[len(clocks) // 2] if clocks else None,
+            'sm_max_mhz': max(top) if top else None,
+            'reasons': sorted(reasons), 'samples': len(clocks)}
+
+
+def cpu_port_gcells(iterate, threads=None):
+  """GCell/s of the CPU oracle on the workload grid, `iterate` iterations."""
+  sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+  import golden
+  if threads:
+    os.environ['OMP_NUM_THREADS'] = str(threads)
+  oracle = golden.Oracle(load_stencil(iterate))
+  inputs = oracle.reference_inputs(WORKLOAD['dims'])
+  _, seconds = oracle.run(inputs, with_seconds=True)
+  cells = WORKLOAD['dims'][0] * WORKLOAD['dims'][1]
+  return cells * iterate / seconds / 1e9, seconds
+
+
+def run_reference(args, rank):
+  """--impl reference: the golden-loop port on the host cores."""
+  if rank != 0:
+    return
+  cores = os.cpu_count() or 1
+  for _ in range(min(args.warmup, 1)):
+    cpu_port_gcells(CPU_SAMPLE_ITERATE, cores)
+  values, total = [], 0.0
+  for _ in range(args.steps):
+    value, seconds = cpu_port_gcells(CPU_SAMPLE_ITERATE, cores)
+    values.append(value)
+    total += seconds
+  value = sum(values) / len(values)
+  sample = '%dx%d float32, %d of %d iterations per step' % (
+      WORKLOAD['dims'] + (CPU_SAMPLE_ITERATE, WORKLOAD['iterate']))
+  print(json.dumps({
+      'impl': 'reference', 'metric': 'stencil_cell_updates_per_second',
+      'value': value, 'unit': 'GCell/s', 'n_gpus': args.gpus,
+      'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+      'data': 'synthetic (reference initialiser, host.py:1033-1051)',
+      'config': workload_config(1),
+      'cpu_baseline': {'value': value, 'unit': 'GCell/s', 'cores': cores,
+                       'kind': 'port', 'sample': sample},
+      'e2e': {'value': value, 'unit': 'GCell/s', 'h2d_bytes_per_step': 0,
+              'd2h_bytes_per_step': 0},
+      'gpu_launches': 0}))
+
+
+def workload_config(n_gpus):
+  d0, d1 = WORKLOAD['dims']
+  return {'workload': 'jacobi2d.soda float32 %dx%d iterate %d (BASELINE '
+                      'configs[1]); per GPU' % (d0, d1, WORKLOAD['iterate']),
+          'global_grid': [d0, d1 * n_gpus], 'iterate': WORKLOAD['iterate'],
+          'partition': 'single GPU' if n_gpus == 1 else
+                       '%d slabs along the streamed dimension, NCCL halo '
+                       'exchange per launch' % n_gpus,
+          'l2': 'inputs (1.07 GB per GPU) exceed the 126 MB L2; no flush'}
+
+
+def main():
+  parser = argparse.ArgumentParser()
+  parser.add_argument('--gpus', type=int, default=1)
+  parser.add_argument('--steps', type=int, default=10)
+  parser.add_argument('--warmup', type=int, default=3)
+  parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  parser.add_argument('--no-cpu-baseline', action='store_true')
+  args = parser.parse_args()
+  rank = int(os.environ.get('RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  if args.impl == 'reference':
+    run_reference(args, rank)
+    return
+  args.warmup = max(args.warmup, 3)
+
+  import numpy as np
+  import torch
+  from soda import cuda as soda_cuda
+  if not torch.cuda.is_available():
+    sys.exit('bench.py: no CUDA device; this backend has no CPU path')
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local_rank)
+  distributed = world > 1
+  if distributed:
+    import torch.distributed as dist
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+  stencil = load_stencil()
+  library = soda_cuda.compile_stencil(stencil)
+  dims = WORKLOAD['dims']
+  cells = dims[0] * dims[1]
+  iterate = WORKLOAD['iterate']
+  shape = (dims[1], dims[0])
+
+  def barrier():
+    torch.cuda.synchronize()
+    if distributed:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(value):
+    if not distributed:
+      return value
+    t = torch.tensor([value], dtype=torch.float64, device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+  # synthetic input: the reference initialiser's pattern (host.py:1033-1051)
+  p = torch.arange(dims[0], device='cuda', dtype=torch.float32)
+  q = torch.arange(dims[1], device='cuda', dtype=torch.float32) + (
+      rank * dims[1] if distributed else 0)
+  total = float(dims[0] + dims[1] * world)
+  dev_in = ((q[:, None] + p[None, :]) / torch.tensor(
+      total, dtype=torch.float32, device='cuda')).contiguous()
+  stream = torch.cuda.current_stream().cuda_stream
+
+  if distributed:
+    from soda import cuda_slab
+    runner = cuda_slab.SlabRunner(library, (dims[0], dims[1] * world), rank,
+                                  world)
+    runner.load_local([dev_in])
+    step = lambda: runner.run(iterate)
+    launches_per_step = runner.launches_per_run(iterate)
+  else:
+    dev_out = torch.empty(shape, dtype=torch.float32, device='cuda')
+    step = lambda: library.run_device([dev_in], [dev_out], dims, iterate,
+                                      stream)
+    launches_per_step = None
+
+  # ---- device-resident timing ------------------------------------------------
+  for _ in range(args.warmup):
+    step()
+  barrier()
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
+  start.record()
+  for _ in range(args.steps):
+    step()
+  stop.record()
+  barrier()
+  clocks = sampler.stop() if sampler else None
+  ms_total = max_over_ranks(start.elapsed_time(stop))
+  ms_per_step = ms_total / args.steps
+  value = cells * world * iterate / (ms_per_step * 1e6)     # GCell/s
+  stats = library.stats
+  if launches_per_step is None:
+    launches_per_step = stats['launches']
+  depth = stats['depth']
+
+  # ---- end to end through the C ABI with host buffers ------------------------
+  host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+  host_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+  host_in.copy_(dev_in)
+  torch.cuda.synchronize()
+  np_in, np_out = host_in.numpy(), host_out.numpy()
+  e2e_steps = max(2, min(args.steps, 5))
+  for _ in range(2):
+    library.run([np_in], [np_out])
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(e2e_steps):
+    library.run([np_in], [np_out])       # H2D + all launches + D2H, synchronous
+  torch.cuda.synchronize()
+  e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+  barrier()
+  e2e_stats = library.stats
+  e2e_value = cells * world * iterate / (e2e_ms * 1e6)
+
+  if rank != 0:
+    if distributed:
+      dist.destroy_process_group()
+    return
+
+  peak, peak_kind = measured_hbm_gbs()
+  launch_ms = ms_per_step / launches_per_step
+  achieved = cells * BYTES_PER_CELL / (launch_ms * 1e6)        # GB/s
+  traffic = None
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as handle:
+      traffic = json.load(handle).get('jacobi2d_d%d' % depth)
+  except (OSError, ValueError):
+    pass
+  result = {
+      'metric': 'stencil_cell_updates_per_second', 'value': value,
+      'unit': 'GCell/s', 'n_gpus': world, 'steps': args.steps,
+      'warmup': args.warmup, 'ms_per_step': ms_per_step,
+      'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'f32',
+      'data': 'synthetic (reference initialiser pattern, host.py:1033-1051)',
+      'config': dict(workload_config(world), temporal_depth=depth,
+                     launches_per_step=launches_per_step,
+                     threads=stats['threads'], smem_bytes=stats['smem_bytes'],
+                     tma=bool(stats['used_tma'])),
+      'e2e': {'value': e2e_value, 'unit': 'GCell/s', 'ms_per_step': e2e_ms,
+              'h2d_bytes_per_step': cells * 4, 'd2h_bytes_per_step': cells * 4,
+              'h2d_ms': e2e_stats['h2d_ms'], 'd2h_ms': e2e_stats['d2h_ms'],
+              'kernel_ms': e2e_stats['kernel_ms'], 'steps': e2e_steps,
+              'api': 'soda_cuda_run (C ABI form of jacobi2d(buffer_t*, '
+                     'buffer_t*, const char*)), pinned host buffers'},
+      'gpu_launches': launches_per_step * args.steps,
+      'roofline': {
+          'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+          'frac': achieved / peak, 'traffic': traffic,
+          'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
+          'kernel': 'soda_jacobi2d_d%d<true>' % depth,
+          'algorithmic_bytes_per_launch': cells * BYTES_PER_CELL,
+          'launch_ms': launch_ms,
+          'note': 'one launch advances %d iterations; the streaming-'
+                  'equivalent rate (8 B x cells x iterate / time) is '
+                  '%.0f GB/s' % (depth, cells * 8 * iterate /
+                                 (ms_per_step * 1e6))},
+      'clocks': clocks,
+  }
+  if not args.no_cpu_baseline and world == 1:
+    cores = os.cpu_count() or 1
+    cpu_value, cpu_seconds = cpu_port_gcells(CPU_SAMPLE_ITERATE, cores)
+    result['cpu_baseline'] = {
+        'value': cpu_value, 'unit': 'GCell/s', 'cores': cores, 'kind': 'port',
+        'seconds': cpu_seconds,
+        'sample': '%dx%d float32, %d of %d iterations (same grid, ping-pong '
+                  'golden loop, g++ -O3 -fopenmp)' % (
+                      dims + (CPU_SAMPLE_ITERATE, iterate))}
+  print(json.dumps(result))
+  if distributed:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

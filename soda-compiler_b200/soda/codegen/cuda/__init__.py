@@ -96,6 +96,7 @@ def check_supported(program):
                              'programs, not %d' % program.dim)
   if len(program.inputs) > 8 or len(program.outputs) > 8:
     raise util.SemanticError('at most 8 inputs and 8 outputs')
+  program.check_windows()
 
 
 def default_vec(program):

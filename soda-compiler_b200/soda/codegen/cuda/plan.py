@@ -131,13 +131,11 @@ class Program:
   def elem_size(self, name):
     return util.get_width_in_bytes(self.types[name])
 
-  def window(self, iterations=None):
-    """``(lo, hi)`` per dimension: bounding box of every offset at which the
-    outputs of ``iterations`` chained iterations read the original inputs —
-    the box of the reference's overall stencil window (core.py:793-830)."""
-    iterations = self.iterate if iterations is None else iterations
+  def _reach(self, iterations):
+    """Per iteration, name -> (lo, hi) box of input offsets, or None."""
     zero = (0,) * self.dim
     reach = {name: (zero, zero) for name in self.input_names}
+    history = []
     for it in range(iterations):
       for stage in self.stages:
         boxes = []
@@ -150,13 +148,43 @@ class Program:
             tuple(min(b[0][d] for b in boxes) for d in range(self.dim)),
             tuple(max(b[1][d] for b in boxes) for d in range(self.dim))
         ) if boxes else None
-      outs = [reach[name] for name in self.output_names if reach[name]]
+      history.append(dict(reach))
       if it + 1 < iterations:
         reach = {name: reach[self.feedback[name]] for name in self.input_names}
+    return history
+
+  def window(self, iterations=None):
+    """``(lo, hi)`` per dimension: bounding box of every offset at which the
+    outputs of ``iterations`` chained iterations read the original inputs —
+    the box of the reference's overall stencil window (core.py:793-830)."""
+    iterations = self.iterate if iterations is None else iterations
+    zero = (0,) * self.dim
+    if iterations == 0:
+      return zero, zero
+    last = self._reach(iterations)[-1]
+    outs = [last[name] for name in self.output_names if last[name]]
     if not outs:
       return zero, zero
     return (tuple(min(o[0][d] for o in outs) for d in range(self.dim)),
             tuple(max(o[1][d] for o in outs) for d in range(self.dim)))
+
+  def check_windows(self):
+    """Every stage's window must contain its own store point in every
+    dimension.  Otherwise the reference's golden loop itself runs out of
+    bounds (its loops start at -min and end at dims-max unclamped,
+    host.py:1082-1091), so there is no defined result to reproduce."""
+    for reach in self._reach(1):
+      for stage in self.stages:
+        box = reach.get(stage.name)
+        if box is None:
+          raise util.SemanticError(
+              '`%s` does not depend on any input' % stage.name)
+        for d in range(self.dim):
+          if box[0][d] > 0 or box[1][d] < 0:
+            raise util.SemanticError(
+                '`%s` only reads inputs at offsets %d..%d from its store '
+                'point in dimension %d: the window must include 0' %
+                (stage.name, box[0][d], box[1][d], d))
 
   def valid_region(self, dims, iterations=None):
     """``[(lo, hi)]`` per dimension where outputs are defined: the bounds of

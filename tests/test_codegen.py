@@ -1,0 +1,126 @@
+"""sodac --cuda-* : the plugin API and the emitted text (no GPU needed)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import common
+from haoda import util
+from soda import core
+from soda.codegen import cuda as codegen
+from soda.codegen.cuda import plan
+
+SODAC = os.path.join(common.ROOT, 'soda-compiler_b200', 'sodac')
+
+
+def sodac(*args, stdin=None):
+  return subprocess.run([sys.executable, SODAC] + list(args), input=stdin,
+                        stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                        text=True, check=False)
+
+
+def test_kernel_and_host_to_files_and_stdout(tmp_path):
+  kernel, host = tmp_path / 'k.cu', tmp_path / 'h.cpp'
+  done = sodac(common.bench_path('blur'), '--cuda-kernel', str(kernel),
+               '--cuda-host', str(host), '--cuda-header', '-')
+  assert done.returncode == 0, done.stderr
+  assert 'int blur(buffer_t *var_input_buffer, buffer_t *var_blur_y_buffer, ' \
+         'const char* xclbin)' in done.stdout
+  text = kernel.read_text()
+  assert '__global__ void __launch_bounds__' in text
+  assert 'soda::tma_load(' in text and 'soda::mbar_wait(' in text
+  # the reference-lowered expressions, operands mapped to register windows
+  assert '/ 3)' in text and text.count('r[k] = (') == 2
+  assert 'int blur(' in host.read_text()
+  assert 'soda_cuda_run' in host.read_text()
+
+
+def test_stdin_and_iterate_override():
+  done = sodac('-', '--iterate', '6', '--cuda-temporal-depth', '4',
+               '--cuda-kernel', '-', stdin=common.bench_text('jacobi2d'))
+  assert done.returncode == 0, done.stderr
+  assert 'soda_jacobi2d_d4(' in done.stdout      # main depth
+  assert 'soda_jacobi2d_d2(' in done.stdout      # remainder 6 % 4
+
+
+def test_errors_exit_1():
+  assert sodac('-', '--cuda-kernel', '-', stdin='kernel: broken').returncode == 1
+  done = sodac(common.bench_path('denoise2d'), '--iterate', '2',
+               '--cuda-kernel', '-')
+  assert done.returncode == 1
+  assert 'number of input tensors must be the same as output' in done.stderr
+
+
+def test_unsupported_programs_raise_semantic_error():
+  text = ('kernel: k\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+          'input %s: a(8, *)\noutput %s: b(0, 0) = a(0, 0)\n')
+  with pytest.raises(util.SemanticError):      # ap_int width
+    codegen.make_schedules(plan.extract_program(
+        core.Stencil.from_text(text % ('int5', 'int5'))))
+  one_d = ('kernel: k\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+           'input float: a\noutput float: b(0) = a(0) + a(1)\n')
+  with pytest.raises(util.SemanticError):
+    codegen.make_schedules(plan.extract_program(core.Stencil.from_text(one_d)))
+
+
+def test_calls_are_routed_through_exact_math_wrappers():
+  import io
+  program = plan.extract_program(common.stencil('denoise2d'))
+  out = io.StringIO()
+  codegen.print_kernel(program, codegen.make_schedules(program), out)
+  assert 'soda_fn_sqrt(' in out.getvalue()
+  assert ' sqrt(' not in out.getvalue().replace('soda_fn_sqrt(', '')
+
+
+def test_print_code_does_not_modify_the_stencil():
+  import argparse
+  stencil = common.stencil('seidel2d', 2)
+  before = [str(t) for t in stencil.tensors.values()]
+  args = argparse.Namespace(cuda_kernel_file=os.devnull,
+                            cuda_host_file=os.devnull)
+  codegen.print_code(stencil, args)
+  assert [str(t) for t in stencil.tensors.values()] == before
+
+
+@pytest.mark.skipif(not common.have_reference(),
+                    reason='needs /root/reference')
+def test_backend_accepts_the_reference_stencil_object(tmp_path):
+  """print_code on the UNMODIFIED reference's Stencil emits the same kernel
+  as on this repo's Stencil (run in a subprocess: package names collide)."""
+  script = tmp_path / 'via_reference.py'
+  script.write_text('''
+import importlib.util, os, sys, collections, collections.abc
+root = %r
+for n in ("Iterable", "Mapping"):
+    setattr(collections, n, getattr(collections.abc, n))
+sys.path[:0] = [os.path.join(root, "oracle", "refshim"), "/root/reference/src"]
+sys.path.append(os.path.join(root, "oracle"))
+import ref_tool
+stencil = ref_tool.load_stencil(sys.argv[1], int(sys.argv[2]))
+# load this repo's backend under private names next to the reference packages
+def load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec); sys.modules[name] = mod
+    spec.loader.exec_module(mod); return mod
+pkg = os.path.join(root, "soda-compiler_b200", "soda", "codegen", "cuda")
+import types
+sys.modules.setdefault("soda.codegen.cuda", types.ModuleType("soda.codegen.cuda"))
+plan = load("soda.codegen.cuda.plan", os.path.join(pkg, "plan.py"))
+kernel = load("soda.codegen.cuda.kernel", os.path.join(pkg, "kernel.py"))
+host = load("soda.codegen.cuda.host", os.path.join(pkg, "host.py"))
+backend = load("soda.codegen.cuda", os.path.join(pkg, "__init__.py"))
+program = plan.extract_program(stencil)
+backend.print_kernel(program, backend.make_schedules(program), sys.stdout)
+''' % common.ROOT)
+  for name, iterate in (('sobel2d', 1), ('jacobi2d', 4), ('denoise3d', 1)):
+    via_reference = subprocess.run(
+        [sys.executable, str(script),
+         os.path.join(common.REFERENCE_DIR, 'tests', 'src', name + '.soda'),
+         str(iterate)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+        text=True, check=False)
+    assert via_reference.returncode == 0, via_reference.stderr[-2000:]
+    ours = sodac(common.bench_path(name), '--iterate', str(iterate),
+                 '--cuda-kernel', '-')
+    assert ours.returncode == 0
+    assert via_reference.stdout == ours.stdout

