@@ -176,6 +176,29 @@ int pick_chunks(long long tile_blocks, long long resident, int rows,
   return best;
 }
 
+// The launches of a run: greedily the deepest compiled variant that still
+// fits the remaining iterations (SODA_CUDA_DEPTH caps the depth).
+int plan_depths(const ProgramDesc& prog, int iterate, std::vector<int>* depths) {
+  int forced = 0;
+  if (const char* v = getenv("SODA_CUDA_DEPTH")) forced = atoi(v);
+  for (int left = iterate; left > 0;) {
+    int pick = 0;
+    for (int i = 0; i < prog.n_variants; ++i) {
+      const int d = prog.variants[i].depth;
+      if (d <= left && (forced <= 0 || d <= forced) && d > pick) pick = d;
+    }
+    if (pick == 0) {
+      fprintf(stderr, "ERROR: no compiled depth fits %d remaining iterations\n",
+              left);
+      return kInternalError;
+    }
+    depths->push_back(pick);
+    left -= pick;
+  }
+  if (depths->size() > 1 && prog.n_in != prog.n_out) return kInternalError;
+  return kSuccess;
+}
+
 }  // namespace
 
 int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
@@ -319,26 +342,10 @@ int run_device(const ProgramDesc& prog, const void* const* inputs,
             prog.app_name, prog.iterate);
     return kInternalError;
   }
-  // plan the launches: greedily the deepest compiled variant that still fits
   std::vector<int> depths;
-  int forced = 0;
-  if (const char* v = getenv("SODA_CUDA_DEPTH")) forced = atoi(v);
-  for (int left = iterate; left > 0;) {
-    int pick = 0;
-    for (int i = 0; i < prog.n_variants; ++i) {
-      const int d = prog.variants[i].depth;
-      if (d <= left && (forced <= 0 || d <= forced) && d > pick) pick = d;
-    }
-    if (pick == 0) {
-      fprintf(stderr, "ERROR: no compiled depth fits %d remaining iterations\n",
-              left);
-      return kInternalError;
-    }
-    depths.push_back(pick);
-    left -= pick;
-  }
+  rc = plan_depths(prog, iterate, &depths);
+  if (rc != kSuccess) return rc;
   const int n_launch = static_cast<int>(depths.size());
-  if (n_launch > 1 && prog.n_in != prog.n_out) return kInternalError;
 
   long long cells = 1;
   for (int d = 0; d < prog.dim; ++d) cells *= dims[d];
@@ -404,6 +411,172 @@ void rewrite(buffer_t* b, int elem, int dim, const int32_t* min,
     if (d < dim) stride *= extent[d];
   }
   b->elem_size = elem;
+}
+
+}  // namespace
+
+namespace {
+
+cudaStream_t g_streams[3];   // h2d, compute, d2h
+bool g_streams_ready = false;
+
+// Host buffers, large problem: cut the streamed dimension into pieces and
+// overlap  H2D(piece k+1) | all launches on piece k | D2H(piece k-1).
+//
+// Every launch j keeps a frontier f_j: its output rows [0, f_j) are done.
+// When input rows [0, avail) are on the device, launch 0 can extend its
+// frontier to avail - reach_hi (to N once everything is loaded), launch 1
+// follows launch 0's frontier the same way, and so on; rows behind the last
+// launch's frontier are final and go back to the host.  No cell is computed
+// twice and every cell sees exactly the operands of the one-shot run, so the
+// result is bit-identical.  The ping-pong buffers are shared between launches
+// j and j-2; holding f_j back by max(reach_hi[j], reach_lo[j-1]) keeps launch
+// j's writes below every row launch j-1 will still read.
+int run_pipelined(const ProgramDesc& prog, buffer_t* const* inputs,
+                  buffer_t* const* outputs, const int32_t* dims,
+                  long long cells, int pieces) {
+  const int s = prog.dim - 1;
+  const int rows = dims[s];
+  const long long row_cells = cells / rows;
+  std::vector<int> depths;
+  int rc = plan_depths(prog, prog.iterate, &depths);
+  if (rc != kSuccess) return rc;
+  const int n_launch = static_cast<int>(depths.size());
+  if (!g_streams_ready) {
+    for (auto& st : g_streams)
+      SODA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking),
+                 kDeviceRunFailed);
+    g_streams_ready = true;
+  }
+  cudaStream_t s_in = g_streams[0], s_run = g_streams[1], s_out = g_streams[2];
+
+  PoolLease lease;
+  void* in_dev[kRtMaxTensors];
+  void* out_dev[kRtMaxTensors];
+  void* scratch[kRtMaxTensors] = {};
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (int k = 0; k < prog.n_in; ++k) {
+      in_dev[k] = lease.get(static_cast<size_t>(cells) * prog.in_elem[k]);
+      if (in_dev[k] == nullptr) return kDeviceMallocFailed;
+    }
+    for (int k = 0; k < prog.n_out; ++k) {
+      out_dev[k] = lease.get(static_cast<size_t>(cells) * prog.out_elem[k]);
+      if (out_dev[k] == nullptr) return kDeviceMallocFailed;
+      if (n_launch > 1) {
+        scratch[k] = lease.get(static_cast<size_t>(cells) * prog.out_elem[k]);
+        if (scratch[k] == nullptr) return kDeviceMallocFailed;
+      }
+    }
+    memset(&g_stats, 0, sizeof(g_stats));
+    g_stats.cells = cells;
+    g_stats.iterate = prog.iterate;
+    g_stats.depth = depths[0];
+    g_stats_pending = false;
+  }
+  // streamed reach of every launch
+  std::vector<int> reach_lo(n_launch), reach_hi(n_launch), hold(n_launch);
+  for (int j = 0; j < n_launch; ++j) {
+    const int* w = prog.window + depths[j] * 2 * kRtMaxDim;
+    reach_lo[j] = std::max(0, -w[s]);
+    reach_hi[j] = std::max(0, w[kRtMaxDim + s]);
+  }
+  for (int j = 0; j < n_launch; ++j)
+    hold[j] = std::max(reach_hi[j], j > 0 ? reach_lo[j - 1] : 0);
+  int32_t full_lo[kRtMaxDim] = {0, 0, 0, 0};
+  int32_t full_hi[kRtMaxDim] = {1, 1, 1, 1};
+  for (int d = 0; d < prog.dim; ++d) full_hi[d] = dims[d];
+  int32_t fin_lo[kRtMaxDim], fin_hi[kRtMaxDim];
+  valid_region(prog, prog.iterate, dims, fin_lo, fin_hi);
+
+  std::vector<int> frontier(n_launch, 0);
+  std::vector<cudaEvent_t> events;
+  auto new_event = [&]() {
+    cudaEvent_t ev;
+    cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    events.push_back(ev);
+    return ev;
+  };
+  SODA_CHECK(cudaEventRecord(g_ev[2], s_in), kCopyToDeviceFailed);
+  SODA_CHECK(cudaEventRecord(g_ev[0], s_run), kDeviceRunFailed);
+  int loaded = 0;
+  for (int piece = 0; piece < pieces; ++piece) {
+    const int upto = static_cast<int>(
+        static_cast<long long>(rows) * (piece + 1) / pieces);
+    if (upto <= loaded) continue;
+    for (int k = 0; k < prog.n_in; ++k) {
+      const size_t off =
+          static_cast<size_t>(loaded) * row_cells * prog.in_elem[k];
+      const size_t bytes =
+          static_cast<size_t>(upto - loaded) * row_cells * prog.in_elem[k];
+      SODA_CHECK(cudaMemcpyAsync(static_cast<char*>(in_dev[k]) + off,
+                                 inputs[k]->host + off, bytes,
+                                 cudaMemcpyHostToDevice, s_in),
+                 kCopyToDeviceFailed);
+    }
+    loaded = upto;
+    cudaEvent_t arrived = new_event();
+    SODA_CHECK(cudaEventRecord(arrived, s_in), kCopyToDeviceFailed);
+    SODA_CHECK(cudaStreamWaitEvent(s_run, arrived, 0), kDeviceRunFailed);
+    if (piece + 1 == pieces)
+      SODA_CHECK(cudaEventRecord(g_ev[3], s_in), kCopyToDeviceFailed);
+
+    int avail = loaded;
+    const int done_before = frontier[n_launch - 1];
+    const void* src[kRtMaxTensors];
+    void* dst[kRtMaxTensors];
+    for (int j = 0; j < n_launch; ++j) {
+      const int target =
+          avail >= rows ? rows : std::max(frontier[j], avail - hold[j]);
+      const bool last = j + 1 == n_launch;
+      const bool to_outputs = ((n_launch - 1 - j) % 2) == 0;
+      for (int k = 0; k < prog.n_in; ++k)
+        src[k] = j == 0 ? in_dev[k]
+                        : (to_outputs ? scratch[k] : out_dev[k]);
+      for (int k = 0; k < prog.n_out; ++k)
+        dst[k] = to_outputs ? out_dev[k] : scratch[k];
+      if (target > frontier[j]) {
+        rc = launch(prog, depths[j], src, dst, dims, frontier[j], target,
+                    last ? fin_lo : full_lo, last ? fin_hi : full_hi, s_run);
+        if (rc != kSuccess) return rc;
+        frontier[j] = target;
+      }
+      avail = frontier[j];
+    }
+    const int done = frontier[n_launch - 1];
+    if (done > done_before) {
+      cudaEvent_t computed = new_event();
+      SODA_CHECK(cudaEventRecord(computed, s_run), kDeviceRunFailed);
+      SODA_CHECK(cudaStreamWaitEvent(s_out, computed, 0), kCopyToHostFailed);
+      if (done_before == 0)
+        SODA_CHECK(cudaEventRecord(g_ev[4], s_out), kCopyToHostFailed);
+      for (int k = 0; k < prog.n_out; ++k) {
+        const size_t off =
+            static_cast<size_t>(done_before) * row_cells * prog.out_elem[k];
+        const size_t bytes = static_cast<size_t>(done - done_before) *
+                             row_cells * prog.out_elem[k];
+        SODA_CHECK(cudaMemcpyAsync(outputs[k]->host + off,
+                                   static_cast<char*>(out_dev[k]) + off, bytes,
+                                   cudaMemcpyDeviceToHost, s_out),
+                   kCopyToHostFailed);
+      }
+    }
+  }
+  SODA_CHECK(cudaEventRecord(g_ev[1], s_run), kDeviceRunFailed);
+  SODA_CHECK(cudaEventRecord(g_ev[5], s_out), kCopyToHostFailed);
+  SODA_CHECK(cudaStreamSynchronize(s_in), kDeviceSyncFailed);
+  SODA_CHECK(cudaStreamSynchronize(s_run), kDeviceSyncFailed);
+  SODA_CHECK(cudaStreamSynchronize(s_out), kDeviceSyncFailed);
+  for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, g_ev[2], g_ev[3]) == cudaSuccess)
+    g_stats.h2d_ms = ms;
+  if (cudaEventElapsedTime(&ms, g_ev[4], g_ev[5]) == cudaSuccess)
+    g_stats.d2h_ms = ms;
+  if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess)
+    g_stats.kernel_ms = ms;
+  g_stats.reserved = pieces;
+  return kSuccess;
 }
 
 }  // namespace
@@ -487,6 +660,29 @@ int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
     rc = ensure_device();
   }
   if (rc != kSuccess) return rc;
+
+  // large all-host problems: overlap the copies with the launches
+  bool all_host = true;
+  size_t moved = 0;
+  for (int k = 0; k < prog.n_in; ++k) {
+    all_host = all_host && inputs[k]->dev == 0;
+    moved += static_cast<size_t>(cells) * prog.in_elem[k];
+  }
+  for (int k = 0; k < prog.n_out; ++k) {
+    all_host = all_host && outputs[k]->dev == 0;
+    moved += static_cast<size_t>(cells) * prog.out_elem[k];
+  }
+  int pieces = static_cast<int>(std::min<size_t>(16, moved >> 27));  // 128 MiB
+  if (const char* v = getenv("SODA_CUDA_PIECES")) pieces = atoi(v);
+  pieces = std::min(pieces, dims[prog.dim - 1]);
+  if (all_host && pieces > 1) {
+    rc = run_pipelined(prog, inputs, outputs, dims, cells, pieces);
+    if (rc == kSuccess && env_flag("SODA_CUDA_VERBOSE"))
+      fprintf(stderr, "INFO: %d pieces: h2d %.3f ms, launches %.3f ms, d2h "
+                      "%.3f ms (overlapped)\n", pieces, g_stats.h2d_ms,
+              g_stats.kernel_ms, g_stats.d2h_ms);
+    return rc;
+  }
 
   cudaStream_t stream = nullptr;
   PoolLease lease;

@@ -153,6 +153,28 @@ def test_reference_harness_accepts_the_cuda_path(name, iterate, dims):
   assert harness.test(dims, on_random_inputs) == 0
 
 
+@pytest.mark.parametrize('case', [
+    ('blur', 1, (1037, 211), {}), ('jacobi2d', 7, (1024, 300), {'depth': 4}),
+    ('jacobi2d', 16, (2048, 260), {'depth': 8}),
+    ('seidel2d', 4, (1280, 160), {'depth': 2}),
+    ('denoise2d', 1, (777, 141), {}), ('heat3d', 3, (192, 48, 33), {'depth': 2}),
+    ('denoise3d', 1, (93, 41, 37), {})], ids=_ids)
+def test_pipelined_host_path_is_bit_identical(case, monkeypatch):
+  """Host buffers are processed in pieces of the streamed dimension with the
+  copies overlapping the launches; any number of pieces gives the bits of the
+  one-shot run."""
+  name, iterate, dims, options = case
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=21)
+  want = orc.run(inputs)
+  library = _library(name, iterate, options)
+  for pieces in ('1', '2', '5', '13'):
+    monkeypatch.setenv('SODA_CUDA_PIECES', pieces)
+    got = library.run(inputs)
+    for g, w in zip(got, want):
+      common.assert_bit_exact(g, w, '%s pieces=%s' % (_ids(case), pieces))
+
+
 def test_bad_elem_size_is_rejected():
   library = _library('jacobi2d', 2, {})
   wrong = [np.zeros((64, 64), dtype=np.float64)]
