@@ -133,7 +133,8 @@ def build(stencil, build_dir=None, options=None, fast_math=False,
     handle.write(kernel_src)
   with open(host_path, 'w') as handle:
     handle.write(host_src)
-  command = nvcc_command([kernel_path, host_path, runtime], lib + '.tmp',
+  tmp = '%s.%d.tmp' % (lib, os.getpid())   # concurrent builders do not collide
+  command = nvcc_command([kernel_path, host_path, runtime], tmp,
                          fast_math, ['-Xptxas', '-v'] if verbose else [])
   done = subprocess.run(command, stdout=subprocess.PIPE,
                         stderr=subprocess.STDOUT, text=True, check=False)
@@ -142,7 +143,7 @@ def build(stencil, build_dir=None, options=None, fast_math=False,
   if done.returncode != 0:
     raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (
         program.app_name, ' '.join(command), done.stdout))
-  os.replace(lib + '.tmp', lib)
+  os.replace(tmp, lib)
   return lib
 
 

@@ -1,0 +1,123 @@
+"""Slab partitioning + halo exchange on CPU: world_size 2 and 3 over gloo.
+
+The kernel launch is replaced by a stand-in built on the CPU oracle (test
+infrastructure) so that what is exercised here is the host logic of
+soda/cuda_slab.py: the partition, ghost zones, which planes travel where, the
+ping-pong of fed-back tensors and the translation of the global valid region.
+The sharded result must equal the single-process result bit for bit.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import common
+
+
+def _free_port():
+  with socket.socket() as sock:
+    sock.bind(('127.0.0.1', 0))
+    return sock.getsockname()[1]
+
+
+class FakeLibrary:
+  """Identity/geometry of a compiled library, taken from the plan (no GPU)."""
+
+  def __init__(self, name, iterate, depths):
+    from soda.codegen.cuda import plan
+    self.program = plan.extract_program(common.stencil(name, iterate))
+    self.dim = self.program.dim
+    self.iterate = iterate
+    self.inputs = list(self.program.inputs)
+    self.outputs = list(self.program.outputs)
+    self.depths = list(depths)
+
+  def window(self, iterate=None):
+    return self.program.window(self.iterate if iterate is None else iterate)
+
+  def valid_region(self, dims, iterate=None):
+    return self.program.valid_region(dims, iterate)
+
+
+def _oracle_compute(name):
+  def compute(depth, inputs, outputs, local_dims, row_begin, row_end,
+              valid_lo, valid_hi):
+    orc = common.oracle(name, depth)
+    results = orc.run([t.numpy() for t in inputs])
+    grids = np.meshgrid(*[np.arange(n) for n in reversed(local_dims)],
+                        indexing='ij')[::-1]
+    inside = np.ones(tuple(reversed(local_dims)), dtype=bool)
+    for coord, lo, hi in zip(grids, valid_lo, valid_hi):
+      inside &= (coord >= lo) & (coord < hi)
+    for out, result in zip(outputs, results):
+      masked = np.where(inside, result, 0).astype(result.dtype)
+      out[row_begin:row_end] = torch.from_numpy(masked[row_begin:row_end])
+  return compute
+
+
+def _worker(rank, world, port, name, iterate, depths, dims, seed, queue):
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  try:
+    from soda import cuda_slab
+    library = FakeLibrary(name, iterate, depths)
+    orc = common.oracle(name, iterate)
+    full = common.random_inputs(orc, dims, seed=seed)
+    runner = cuda_slab.SlabRunner(library, dims, rank, world,
+                                  compute=_oracle_compute(name))
+    owned = [torch.from_numpy(a[runner.begin:runner.end].copy()) for a in full]
+    runner.load_local(owned)
+    outs = runner.run(iterate)
+    queue.put((rank, runner.begin, runner.end,
+               [o.numpy().copy() for o in outs]))
+    dist.barrier()
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('name,iterate,depths,dims,world', [
+    ('jacobi2d', 6, (2,), (40, 37), 2),
+    ('jacobi2d', 7, (4, 3), (33, 50), 3),
+    ('seidel2d', 4, (2,), (36, 41), 2),
+    ('heat3d', 3, (2, 1), (14, 12, 23), 2),
+    ('blur', 1, (1,), (30, 29), 3),            # one-sided window [0, +2]
+    ('denoise2d', 1, (1,), (28, 31), 2),       # 2 inputs, no feedback
+])
+def test_sharded_equals_single_process(name, iterate, depths, dims, world):
+  for depth in set(depths) | {iterate}:
+    common.oracle(name, depth)        # build once, before the ranks race
+  ctx = mp.get_context('spawn')
+  queue = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(
+      rank, world, port, name, iterate, depths, dims, 17, queue))
+           for rank in range(world)]
+  for proc in procs:
+    proc.start()
+  pieces = [queue.get(timeout=120) for _ in procs]
+  for proc in procs:
+    proc.join(timeout=60)
+    assert proc.exitcode == 0
+  orc = common.oracle(name, iterate)
+  want = orc.run(common.random_inputs(orc, dims, seed=17))
+  for k, expected in enumerate(want):
+    got = np.zeros_like(expected)
+    for _, begin, end, outs in pieces:
+      got[begin:end] = outs[k]
+    common.assert_bit_exact(got, expected, '%s world %d' % (name, world))
+
+
+def test_partition_and_refusals():
+  from soda import cuda_slab
+  assert cuda_slab.partition(10, 3) == [(0, 3), (3, 6), (6, 10)]
+  library = FakeLibrary('jacobi2d', 4, (4,))
+  with pytest.raises(ValueError):      # slabs thinner than the halo
+    cuda_slab.SlabRunner(library, (32, 6), 0, 2, compute=lambda *a: None)
+  if not torch.cuda.is_available():
+    with pytest.raises(RuntimeError):  # no CPU fallback on the product path
+      cuda_slab.SlabRunner(library, (32, 64), 0, 2)

@@ -1,0 +1,84 @@
+"""Multi-GPU slabs on real devices: NCCL halo exchange, bit-identical result.
+
+Needs >= 2 GPUs (``gpurun --gpus 2``); skipped on a single-GPU box.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+  with socket.socket() as sock:
+    sock.bind(('127.0.0.1', 0))
+    return sock.getsockname()[1]
+
+
+def _worker(rank, world, port, name, iterate, options, dims, queue):
+  import torch.distributed as dist
+  os.environ['MASTER_ADDR'] = '127.0.0.1'
+  os.environ['MASTER_PORT'] = str(port)
+  torch.cuda.set_device(rank)
+  dist.init_process_group('nccl', rank=rank, world_size=world,
+                          device_id=torch.device('cuda', rank))
+  try:
+    from soda import cuda as soda_cuda, cuda_slab
+    from soda.codegen import cuda as codegen
+    library = soda_cuda.compile_stencil(common.stencil(name, iterate),
+                                        options=codegen.Options(**options))
+    orc = common.oracle(name, iterate)
+    full = common.random_inputs(orc, dims, seed=23)
+    runner = cuda_slab.SlabRunner(library, dims, rank, world)
+    runner.load_local([torch.from_numpy(a[runner.begin:runner.end].copy()
+                                        ).cuda() for a in full])
+    for _ in range(2):          # running twice must give the same answer
+      outs = runner.run(iterate)
+    torch.cuda.synchronize()
+    queue.put((rank, runner.begin, runner.end,
+               [o.cpu().numpy().copy() for o in outs]))
+    dist.barrier()
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('name,iterate,options,dims', [
+    ('jacobi2d', 16, {'depth': 4}, (2048, 700)),
+    ('jacobi2d', 7, {'depth': 4}, (1030, 333)),
+    ('heat3d', 4, {'depth': 2}, (128, 64, 90)),
+    ('blur', 1, {}, (1037, 211)),
+    ('denoise2d', 1, {}, (1024, 200)),
+])
+def test_sharded_equals_oracle(name, iterate, options, dims):
+  world = min(torch.cuda.device_count(), 4)
+  if world < 2:
+    pytest.skip('needs at least 2 GPUs')
+  import torch.multiprocessing as mp
+  from soda import cuda as soda_cuda
+  from soda.codegen import cuda as codegen
+  soda_cuda.build(common.stencil(name, iterate),
+                  options=codegen.Options(**options))
+  orc = common.oracle(name, iterate)
+  ctx = mp.get_context('spawn')
+  queue = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(
+      rank, world, port, name, iterate, options, dims, queue))
+           for rank in range(world)]
+  for proc in procs:
+    proc.start()
+  pieces = [queue.get(timeout=300) for _ in procs]
+  for proc in procs:
+    proc.join(timeout=60)
+    assert proc.exitcode == 0
+  want = orc.run(common.random_inputs(orc, dims, seed=23))
+  for k, expected in enumerate(want):
+    got = np.zeros_like(expected)
+    for _, begin, end, outs in pieces:
+      got[begin:end] = outs[k]
+    common.assert_bit_exact(got, expected, '%s on %d GPUs' % (name, world))

@@ -31,10 +31,38 @@ def parse_case(text):
   return name, iterate, dims, options
 
 
+def time_e2e(library, dims, reps):
+  """ms per call of library.run on pinned host arrays (H2D + run + D2H)."""
+  import time
+  shape = tuple(reversed(dims))
+  pin = lambda t: torch.empty(shape, dtype=torch.from_numpy(np.empty(
+      0, soda_cuda.NUMPY_TYPES[t])).dtype, pin_memory=True)
+  ins = [pin(t) for _, t in library.inputs]
+  for x in ins:
+    x.copy_(torch.rand(shape) if x.dtype.is_floating_point else
+            torch.randint(0, 30000, shape).to(x.dtype))
+  outs = [pin(t) for _, t in library.outputs]
+  np_in, np_out = [x.numpy() for x in ins], [x.numpy() for x in outs]
+  for _ in range(2):
+    library.run(np_in, np_out)
+  times = []
+  for _ in range(reps):
+    t0 = time.perf_counter()
+    library.run(np_in, np_out)
+    times.append((time.perf_counter() - t0) * 1e3)
+  return float(np.median(times)), library.stats
+
+
+def _unused():
+  name = iterate = dims = options = None
+  return name, iterate, dims, options
+
+
 def main():
   reps = int(os.environ.get('REPS', '5'))
   for text in sys.argv[1:]:
     name, iterate, dims, options = parse_case(text)
+    e2e = options.pop('e2e', 0)
     with open(os.path.join(ROOT, 'benchmarks', name + '.soda')) as handle:
       stencil = core.Stencil.from_text(handle.read(), iterate=iterate)
     try:
@@ -42,6 +70,16 @@ def main():
                                           options=codegen.Options(**options))
     except Exception as e:   # pylint: disable=broad-except
       print('%-50s build failed: %s' % (text, str(e)[:300]))
+      continue
+    if e2e:
+      ms, stats = time_e2e(library, dims, reps)
+      print('%-50s e2e %8.3f ms  %8.1f GCell/s  pieces %s h2d %.2f run %.2f '
+            'd2h %.2f launches %d' % (
+                text, ms, float(np.prod(dims)) * iterate / ms / 1e6,
+                os.environ.get('SODA_CUDA_PIECES', 'auto'), stats['h2d_ms'],
+                stats['kernel_ms'], stats['d2h_ms'], stats['launches']),
+            flush=True)
+      library.release()
       continue
     shape = tuple(reversed(dims))
     dtype = {1: torch.uint8, 2: torch.int16, 4: torch.float32,
