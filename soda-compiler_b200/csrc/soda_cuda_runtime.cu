@@ -254,7 +254,7 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
   }
   args.vec_store = aligned ? 1 : 0;
 
-  if (tma_ok) {
+  if (tma_ok && kv->uses_tma) {
     for (int k = 0; k < prog.n_in; ++k) {
       cuuint64_t gdim[kRtMaxDim];
       cuuint64_t gstride[kRtMaxDim];
@@ -300,29 +300,33 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
   const long long resident =
       static_cast<long long>(per_sm) * g_device.sm_count;
   const int rows = row_end - row_begin;
-  int chunks = pick_chunks(tile_blocks, resident, rows,
-                           kv->lead + kv->out_delay);
+  // 2-D register kernels pack `tiles_per_block` independent strips in a block
+  const int per_block = std::max(1, kv->tiles_per_block);
+  const long long grid_x = (tile_blocks + per_block - 1) / per_block;
+  int chunks = pick_chunks(grid_x, resident, rows, kv->lead + kv->out_delay);
   if (const char* forced = getenv("SODA_CUDA_CHUNKS"))
     chunks = std::max(1, std::min(rows, atoi(forced)));
   args.chunk_rows = (rows + chunks - 1) / chunks;
   chunks = (rows + args.chunk_rows - 1) / args.chunk_rows;
 
-  dim3 grid(static_cast<unsigned>(tile_blocks), static_cast<unsigned>(chunks));
+  dim3 grid(static_cast<unsigned>(grid_x), static_cast<unsigned>(chunks));
   dim3 block(kv->threads);
   void* params[] = {&args};
   SODA_CHECK(cudaLaunchKernel(fn, grid, block, params, kv->smem_bytes, stream),
              kDeviceRunFailed);
   g_stats.launches += 1;
   g_stats.used_tma = tma_ok ? 1 : 0;
-  g_stats.blocks = static_cast<int32_t>(tile_blocks * chunks);
+  g_stats.blocks = static_cast<int32_t>(grid_x * chunks);
   g_stats.threads = kv->threads;
   g_stats.smem_bytes = kv->smem_bytes;
   if (env_flag("SODA_CUDA_VERBOSE"))
     fprintf(stderr,
             "INFO: %s depth %d: grid %lld x %d (%d blocks/SM resident), "
             "%d threads, %d B smem, %s, rows [%d, %d) in chunks of %d\n",
-            prog.app_name, depth, tile_blocks, chunks, per_sm, kv->threads,
-            kv->smem_bytes, tma_ok ? "TMA" : "plain loads", row_begin, row_end,
+            prog.app_name, depth, grid_x, chunks, per_sm, kv->threads,
+            kv->smem_bytes,
+            !tma_ok ? "plain loads" : kv->uses_tma ? "TMA" : "128-bit loads",
+            row_begin, row_end,
             args.chunk_rows);
   return kSuccess;
 }

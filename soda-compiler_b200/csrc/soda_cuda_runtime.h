@@ -35,8 +35,11 @@ struct KernelVariant {
   int smem_bytes;
   int box0;                     // TMA box extent along dim 0
   int boxes_per_row;
-  const void* kernel_tma;       // __global__ void(StreamArgs), TMA input path
-  const void* kernel_plain;     // same, plain-load input path
+  int tiles_per_block;          // 2-D register kernels: strips (warps) per block
+  int uses_tma;                 // the first kernel below needs tensor maps
+  const void* kernel_tma;       // __global__ void(StreamArgs): TMA / aligned
+                                // 128-bit input path
+  const void* kernel_plain;     // same, any alignment
 };
 
 struct ProgramDesc {

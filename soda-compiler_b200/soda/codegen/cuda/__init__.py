@@ -25,6 +25,7 @@ import tempfile
 from haoda import util
 from soda.codegen.cuda import host as host_mod
 from soda.codegen.cuda import kernel as kernel_mod
+from soda.codegen.cuda import kernel_reg as kernel_reg_mod
 from soda.codegen.cuda import plan as plan_mod
 
 SUPPORTED_TYPES = {
@@ -57,16 +58,21 @@ def add_arguments(parser):
       help='cells per thread per vector access along dimension 0')
   parser.add_argument(
       '--cuda-prefetch', type=int, dest='cuda_prefetch', metavar='N',
-      help='input planes requested ahead by TMA')
+      help='input planes requested ahead of the one being consumed')
+  parser.add_argument(
+      '--cuda-style', type=str, dest='cuda_style', choices=['reg', 'ring'],
+      help='kernel family: `reg` keeps the streamed window of every tensor '
+      'in registers and shares dimension-0 neighbours by warp shuffle '
+      '(default); `ring` keeps every tensor in a shared-memory plane ring')
 
 
 class Options:
   """Tuning knobs of the backend; None means "choose for me"."""
 
   def __init__(self, depth=None, tile=None, threads=None, vec=None,
-               prefetch=None):
+               prefetch=None, style=None):
     self.depth, self.tile, self.threads = depth, tile, threads
-    self.vec, self.prefetch = vec, prefetch
+    self.vec, self.prefetch, self.style = vec, prefetch, style
 
   @classmethod
   def from_args(cls, args):
@@ -74,12 +80,13 @@ class Options:
                tile=getattr(args, 'cuda_tile', None),
                threads=getattr(args, 'cuda_threads', None),
                vec=getattr(args, 'cuda_vec', None),
-               prefetch=getattr(args, 'cuda_prefetch', None))
+               prefetch=getattr(args, 'cuda_prefetch', None),
+               style=getattr(args, 'cuda_style', None))
 
   def key(self):
-    return 'd%s_t%s_n%s_v%s_p%s' % (
+    return 'd%s_t%s_n%s_v%s_p%s_%s' % (
         self.depth, 'x'.join(map(str, self.tile)) if self.tile else None,
-        self.threads, self.vec, self.prefetch)
+        self.threads, self.vec, self.prefetch, self.style)
 
 
 def check_supported(program):
@@ -113,9 +120,70 @@ def _default_tiles(program, vec):
   return [(8 * vec, 8, 4), (8 * vec, 4, 4)]
 
 
+def layout_of(sched):
+  """Shared-memory layout of a schedule (by kernel family)."""
+  if sched.style == 'reg':
+    return kernel_reg_mod.Layout(sched)
+  return kernel_mod.Layout(sched)
+
+
+def _make_reg_schedule(program, depth, options, limit):
+  """Register-streaming schedule: the caller's knobs where given, otherwise
+  the candidate with the least halo overhead that fits."""
+  vec = options.vec or min(default_vec(program), 8)
+  if program.dim == 2:
+    warps = (options.threads or 128) // 32
+    prefetch = options.prefetch if options.prefetch is not None else (
+        4 if depth <= 2 else 3 if depth <= 4 else 2)
+    return plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch)
+  if options.tile:
+    if options.tile[0] != 32 * vec:
+      raise util.SemanticError('register-streaming tiles are 32 x vec = %d '
+                               'cells wide' % (32 * vec))
+    rests = [tuple(options.tile[1:])]
+  elif program.dim == 3:
+    rests = [(32,), (16,), (8,)]
+  else:
+    rests = [(8, 4), (4, 4)]
+  prefetches = ([options.prefetch] if options.prefetch is not None
+                else [2, 1])
+  best, problem = None, None
+  for rest in rests:
+    rows = math.prod(rest)
+    for prefetch in prefetches:
+      warps = (options.threads // 32 if options.threads
+               else max(1, min(16, rows // 2)))
+      try:
+        sched = plan_mod.RegSchedule(program, depth, vec, warps, rest,
+                                     prefetch)
+        total = kernel_reg_mod.Layout(sched).total
+      except util.SemanticError as e:
+        problem = problem or e
+        continue
+      if total > limit:
+        problem = problem or util.SemanticError(
+            'depth %d with tile %s needs %d bytes of shared memory (limit '
+            '%d)' % (depth, sched.tile, total, limit))
+        continue
+      score = math.prod(sched.own) / math.prod(sched.tile)
+      if best is None or score > best[0] + 1e-9:
+        best = (score, sched)
+      break
+  if best is None:
+    raise problem
+  return best[1]
+
+
 def make_schedule(program, depth, options, limit=SMEM_LIMIT):
   """The schedule for ``depth`` fused iterations: the caller's knobs where
   given, otherwise the first candidate that fits in shared memory."""
+  if options.style in (None, 'reg'):
+    try:
+      return _make_reg_schedule(program, depth, options,
+                                min(limit, SMEM_LIMIT // 2))
+    except util.SemanticError:
+      if options.style == 'reg':
+        raise
   vec = options.vec or default_vec(program)
   tiles = [tuple(options.tile)] if options.tile else _default_tiles(program,
                                                                     vec)
@@ -149,6 +217,8 @@ def make_schedules(program, options=None):
     main = max(1, min(options.depth, iterate))
   elif not program.feedback or iterate == 1:
     main = 1
+  elif options.style in (None, 'reg') and program.dim == 2:
+    main = min(iterate, 4)
   else:
     main = 1
     for depth in (2, 4, 8, 16):
@@ -176,7 +246,8 @@ def print_kernel(program, schedules, kernel_file):
   p.println('#include "soda_cuda_device.cuh"')
   p.println('#include "soda_cuda_runtime.h"')
   p.println()
-  layouts = [kernel_mod.emit_kernel(p, sched) for sched in schedules]
+  layouts = [(kernel_reg_mod if sched.style == 'reg' else kernel_mod)
+             .emit_kernel(p, sched) for sched in schedules]
   host_mod.emit_variant_table(p, program.app_name, schedules, layouts)
 
 

@@ -1,0 +1,556 @@
+"""Emit the register-streaming sm_100a kernel of a SODA program.
+
+The kernel realises a ``plan.RegSchedule``: every thread walks the streamed
+dimension with ``vec`` cells of its own, keeps the last few planes of every
+tensor of the fused chain it needs again in **registers**, takes dimension-0
+neighbours from the adjacent lanes with **warp shuffles**, and goes through
+shared memory only for neighbours in the other tiled dimensions (3-D: y +- 1).
+Per stage the reference-lowered expression (``Node.c_expr`` with Refs swapped
+for storage, the recipe of the golden loop's ``mutate_load_for_host``,
+reference src/soda/codegen/xilinx/host.py:1093-1117; FPGA counterpart
+src/soda/codegen/xilinx/hls_kernel.py:487-489) is spliced in once per cell of
+the thread's vector.
+
+2-D programs  no shared memory, no barrier.  A block is ``warps`` independent
+              strips of 32 x vec cells; input rows are fetched ``prefetch``
+              rows ahead with 128-bit ``ld.global.nc`` straight into the
+              history registers; outputs leave with 128-bit streaming stores.
+3-D programs  input planes arrive by TMA (cp.async.bulk.tensor + mbarrier) in
+              a shared ring as in kernel.py; each thread copies its own cells
+              of the newest plane into its history; stages whose results are
+              read at y +- 1 also write a shared plane; one __syncthreads()
+              per step.
+
+The streamed loop is unrolled ``period`` times so that history slots are
+compile-time register names: the row computed k steps ago sits in slot
+``(phase - k) mod period``.
+"""
+import collections
+
+from haoda import util
+from soda.codegen.cuda import plan as plan_mod
+
+_TMA_MAX_BOX = 256
+
+
+def kernel_name(sched):
+  return 'soda_%s_d%d' % (sched.program.app_name, sched.depth)
+
+
+class Layout:
+  """Dynamic shared memory of a register-streaming kernel (3-D only)."""
+
+  def __init__(self, sched):
+    self.sched = sched
+    self.guard = -(-sched.guard_elems * 8 // 128) * 128
+    self.ring_depth = {}
+    self.ring_offset = {}
+    loaded = [n for n in sched.inputs if n.ring_depth]
+    self.in_depth = max([n.ring_depth for n in loaded] + [1])
+    offset = self.guard
+    for node in sched.nodes:
+      if not node.ring_depth:
+        continue
+      depth = self.in_depth if node.is_input else node.ring_depth
+      self.ring_depth[node.index] = depth
+      self.ring_offset[node.index] = offset
+      ring = depth * sched.plane_elems * node.elem_size
+      offset += -(-ring // 128) * 128
+    offset += self.guard
+    self.bar_offset = offset
+    if loaded:
+      offset += -(-8 * self.in_depth // 128) * 128
+    self.total = offset if self.ring_offset else 0
+    self.loaded_inputs = loaded
+    self.plane_bytes = {n.index: sched.plane_elems * n.elem_size
+                        for n in loaded}
+    self.box0 = sched.tile[0]
+    self.boxes_per_row = 1
+    if loaded:
+      if sched.tile[0] > _TMA_MAX_BOX:
+        raise util.SemanticError('tile width %d exceeds the TMA box limit' %
+                                 sched.tile[0])
+      for extent in sched.tile[1:]:
+        if extent > _TMA_MAX_BOX:
+          raise util.SemanticError('tile extent %d exceeds the TMA box limit'
+                                   % extent)
+
+
+def _log2(n):
+  return n.bit_length() - 1
+
+
+def _render(stage, ref_code, k):
+  """``(let lines, expression)`` of cell ``k`` of the thread's vector."""
+  let_names = {let.name for let in stage.lets}
+
+  def swap(obj, _):
+    kind = type(obj).__name__
+    if kind == 'Ref':
+      return plan_mod.Code(ref_code(stage.load_of(obj), k))
+    if kind == 'Call' and not obj.name.startswith('soda_fn_'):
+      obj.name = 'soda_fn_' + obj.name
+    elif kind == 'Var' and obj.name in let_names:
+      obj.name = 'let_' + obj.name
+    return obj
+  lets = ['const %s let_%s = %s;' % (
+      let.c_type, let.name, plan_mod.strip_parens(let.expr.visit(swap).c_expr))
+          for let in stage.lets]
+  return lets, stage.expr.visit(swap).c_expr
+
+
+class _Emitter:
+
+  def __init__(self, p, sched):
+    self.p = p
+    self.sched = sched
+    self.lay = Layout(sched)
+    self.s = sched.sdim
+    self.V = sched.vec
+    self.NT = sched.threads
+    self.VPT = sched.vecs_per_thread
+    self.U = sched.period
+    self.P = sched.prefetch
+    self.PLANE = sched.plane_elems
+    self.flat = sched.sdim == 1          # 2-D program: registers only
+    self.DIN = self.lay.in_depth
+
+  # ---- naming ---------------------------------------------------------------
+  def hist(self, node, phase, age):
+    """Register array holding the row of ``node`` that is ``age`` steps old."""
+    return 'h_%s_%d' % (node.ident, (phase - age) % self.U)
+
+  def ring_slot(self, node, age):
+    depth = self.lay.ring_depth[node.index]
+    return '((ii - (%d)) & %d)' % (age, depth - 1)
+
+  # ---- pieces ----------------------------------------------------------------
+  def emit(self):
+    p, sched, lay, s, V = self.p, self.sched, self.lay, self.s, self.V
+    name = kernel_name(sched)
+    p.println('// %s' % sched.describe().replace('\n', '\n// '))
+    p.println('template <bool kTma>')
+    p.println('__global__ void __launch_bounds__(%d) %s(' % (self.NT, name))
+    p.println('    const __grid_constant__ soda::StreamArgs a)')
+    p.do_scope()
+    if lay.total:
+      p.println('extern __shared__ __align__(1024) unsigned char smem_raw[];')
+      for node in sched.nodes:
+        if node.index in lay.ring_offset:
+          p.println('%s* const ring_%s = reinterpret_cast<%s*>(smem_raw + %d);'
+                    '  // %d planes' % (node.c_type, node.ident, node.c_type,
+                                        lay.ring_offset[node.index],
+                                        lay.ring_depth[node.index]))
+      if lay.loaded_inputs:
+        p.println('uint64_t* const bars = reinterpret_cast<uint64_t*>('
+                  'smem_raw + %d);' % lay.bar_offset)
+    p.println('const int tid = threadIdx.x;')
+    p.println('const int lane = tid & 31;')
+    p.println('(void)lane;')
+    p.println()
+    self.emit_geometry()
+    self.emit_histories()
+    if self.flat:
+      self.emit_flat_prologue()
+    else:
+      self.emit_tma_prologue()
+    p.println('for (int i = 0; i < steps; i += %d)' % self.U)
+    p.do_scope()
+    for phase in range(self.U):
+      if phase:
+        p.println('if (i + %d >= steps) break;' % phase)
+      p.println('// ---- phase %d of %d' % (phase, self.U))
+      p.do_scope()
+      p.println('const int ii = i + %d;' % phase)
+      self.emit_step(phase)
+      p.un_scope()
+    p.un_scope()
+    p.un_scope()
+    p.println()
+    return lay
+
+  def emit_geometry(self):
+    p, sched, s, V, VPT = self.p, self.sched, self.s, self.V, self.VPT
+    if self.flat:
+      p.println('// this warp: one strip of dimension 0, one chunk of the '
+                'streamed dimension')
+      p.println('const int strip = blockIdx.x * %d + (tid >> 5);' %
+                sched.tiles_per_block)
+      p.println('if (strip >= a.tiles[0]) return;   // whole warps; no block '
+                'barrier in this kernel')
+      p.println('const int org0 = strip * %d - %d;' % (
+          sched.own[0], sched.tile_halo_lo[0]))
+    else:
+      p.println('// this block: one tile of the non-streamed dims, one chunk '
+                'of the streamed dim')
+      p.println('int tile_rest = blockIdx.x;')
+      for d in range(s):
+        p.println('const int org%d = (tile_rest %% a.tiles[%d]) * %d - %d;' % (
+            d, d, sched.own[d], sched.tile_halo_lo[d]))
+        if d + 1 < s:
+          p.println('tile_rest /= a.tiles[%d];' % d)
+    p.println('const int r0 = a.row_begin + blockIdx.y * a.chunk_rows;')
+    p.println('const int r1 = min(a.row_end, r0 + a.chunk_rows);')
+    p.println('const int base = r0 - %d;   // streamed coordinate of step 0' %
+              sched.lead)
+    p.println('const int steps = (r1 - r0) + %d;' %
+              (sched.lead + sched.out_delay))
+    p.println()
+    p.println('// per-thread vectors: position in the plane, offset in HBM, '
+              'cells this tile')
+    p.println('// owns (store) and cells in the valid region (else 0)')
+    p.println('int pos[%d];' % VPT)
+    p.println('long long goff[%d];' % VPT)
+    p.println('unsigned own[%d], val[%d];' % (VPT, VPT))
+    p.println('bool xin[%d];   // the vector lies inside the grid in the tiled '
+              'dims' % VPT)
+    p.println('int gx[%d];' % VPT)
+    for d in range(1, s):
+      p.println('int gc%d[%d];' % (d, VPT))
+    p.println('#pragma unroll')
+    p.println('for (int j = 0; j < %d; ++j)' % VPT)
+    p.do_scope()
+    if self.flat:
+      p.println('const int q = lane;')
+    else:
+      p.println('const int q = tid + j * %d;' % self.NT)
+    p.println('pos[j] = q * %d;' % V)
+    p.println('const int c0 = (q & 31) * %d;' % V)
+    p.println('int rest = q >> 5;')
+    for d in range(1, s):
+      p.println('const int c%d = rest %% %d;' % (d, sched.tile[d]))
+      if d + 1 < s:
+        p.println('rest /= %d;' % sched.tile[d])
+    p.println('(void)rest;')
+    p.println('gx[j] = org0 + c0;')
+    p.println('long long off = gx[j];')
+    p.println('bool mine = true, ok = true, inside = true;')
+    for d in range(1, s):
+      p.println('gc%d[j] = org%d + c%d;' % (d, d, d))
+      p.println('off += gc%d[j] * a.stride[%d];' % (d, d))
+      p.println('mine = mine && c%d >= %d && c%d < %d && gc%d[j] < a.dims[%d];'
+                % (d, sched.tile_halo_lo[d], d,
+                   sched.tile[d] - sched.tile_halo_hi[d], d, d))
+      p.println('ok = ok && gc%d[j] >= a.valid_lo[%d] && gc%d[j] < '
+                'a.valid_hi[%d];' % (d, d, d, d))
+      p.println('inside = inside && gc%d[j] >= 0 && gc%d[j] < a.dims[%d];' % (
+          d, d, d))
+    p.println('goff[j] = off;')
+    p.println('xin[j] = inside && gx[j] >= 0 && gx[j] + %d <= a.dims[0];' % V)
+    p.println('unsigned m = 0, v = 0;')
+    p.println('#pragma unroll')
+    p.println('for (int k = 0; k < %d; ++k)' % V)
+    p.do_scope()
+    p.println('const int x = gx[j] + k;')
+    p.println('if (mine && c0 + k >= %d && c0 + k < %d && x < a.dims[0]) '
+              'm |= 1u << k;' % (sched.tile_halo_lo[0],
+                                 sched.tile[0] - sched.tile_halo_hi[0]))
+    p.println('if (ok && x >= a.valid_lo[0] && x < a.valid_hi[0]) v |= 1u << k;')
+    p.un_scope()
+    p.println('own[j] = m;')
+    p.println('val[j] = v;')
+    p.un_scope()
+    p.println()
+
+  def emit_histories(self):
+    p, sched = self.p, self.sched
+    p.println('// register histories: slot (phase - age) mod %d holds the row '
+              'computed `age` steps ago' % self.U)
+    for node in sched.nodes:
+      if node.hist_oldest is None:
+        continue
+      for slot in range(self.U):
+        p.println('%s h_%s_%d[%d][%d] = {};' % (
+            node.c_type, node.ident, slot, self.VPT, self.V))
+    p.println()
+
+  # ---- 2-D input path: straight from HBM into the history --------------------
+  def emit_row_load(self, phase, rel_code, age):
+    """Fetch row ``base + rel`` of every input into the slot of ``age``."""
+    p, sched, V = self.p, self.sched, self.V
+    p.println('const int lrow = base + (%s);' % rel_code)
+    p.println('const bool lrow_in = lrow >= 0 && lrow < a.dims[%d];' % self.s)
+    for node in sched.inputs:
+      if node.hist_oldest is None:
+        continue
+      dst = '%s[0]' % self.hist(node, phase, age)
+      p.println('const %s* const src%d = static_cast<const %s*>('
+                'a.in_ptr[%d]) + lrow * a.stride[%d] + goff[0];' % (
+                    node.c_type, node.input_index, node.c_type,
+                    node.input_index, self.s))
+      p.println('if (kTma)')
+      p.do_scope()
+      p.println('if (lrow_in && xin[0]) soda::ld_stream<%s, %d>(%s, src%d);' % (
+          node.c_type, V, dst, node.input_index))
+      p.println('else soda::fill_zero<%s, %d>(%s);' % (node.c_type, V, dst))
+      p.un_scope()
+      p.println('else')
+      p.do_scope()
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      p.println('  %s[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
+                'a.dims[0]) ? src%d[k] : %s(0);' % (
+                    dst, node.input_index, node.c_type))
+      p.un_scope()
+
+  def emit_flat_prologue(self):
+    p = self.p
+    p.println('// rows 0 .. %d of this chunk are in flight before the loop '
+              'starts' % (self.P - 1))
+    for rel in range(self.P):
+      p.do_scope()
+      # step `rel` will find this row at age 0, i.e. in slot rel mod period
+      self.emit_row_load(rel, '%d' % rel, 0)
+      p.un_scope()
+    p.println()
+
+  # ---- 3-D input path: TMA into a shared ring --------------------------------
+  def tma_issue(self, rel_code):
+    p, lay, s = self.p, self.lay, self.s
+    p.println('uint64_t* const bar = &bars[(%s) & %d];' % (rel_code,
+                                                           self.DIN - 1))
+    p.println('soda::mbar_expect_tx(bar, %d);' % sum(lay.plane_bytes.values()))
+    for node in lay.loaded_inputs:
+      coords = ['org%d' % d for d in range(s)] + ['base + (%s)' % rel_code]
+      p.println('soda::tma_load(ring_%s + ((%s) & %d) * %d, &a.in_map[%d], '
+                'bar, %s);' % (node.ident, rel_code, self.DIN - 1, self.PLANE,
+                               node.input_index, ', '.join(coords)))
+
+  def plain_load(self, rel_code):
+    p, lay, s, V = self.p, self.lay, self.s, self.V
+    p.println('const int lrow = base + (%s);' % rel_code)
+    p.println('const bool lrow_in = lrow >= 0 && lrow < a.dims[%d];' % s)
+    for node in lay.loaded_inputs:
+      p.println('#pragma unroll')
+      p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
+      p.do_scope()
+      p.println('%s t[%d];' % (node.c_type, V))
+      cond = ' && '.join(['lrow_in'] + [
+          'gc%d[j] >= 0 && gc%d[j] < a.dims[%d]' % (d, d, d)
+          for d in range(1, s)])
+      p.println('const bool in = %s;' % cond)
+      p.println('const %s* src = static_cast<const %s*>(a.in_ptr[%d]) + '
+                'lrow * a.stride[%d] + goff[j];' % (
+                    node.c_type, node.c_type, node.input_index, s))
+      p.println('if (in && a.vec_store && gx[j] >= 0 && gx[j] + %d <= '
+                'a.dims[0])' % V)
+      p.do_scope()
+      p.println('soda::ld_pack<%s, %d>(t, src);' % (node.c_type, V))
+      p.un_scope()
+      p.println('else')
+      p.do_scope()
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      p.println('  t[k] = (in && gx[j] + k >= 0 && gx[j] + k < a.dims[0]) ? '
+                'src[k] : %s(0);' % node.c_type)
+      p.un_scope()
+      p.println('soda::st_pack<%s, %d>(ring_%s + ((%s) & %d) * %d + pos[j], '
+                't);' % (node.c_type, V, node.ident, rel_code, self.DIN - 1,
+                         self.PLANE))
+      p.un_scope()
+
+  def emit_tma_prologue(self):
+    p, lay = self.p, self.lay
+    if not lay.loaded_inputs:
+      return
+    p.println('if (kTma)')
+    p.do_scope()
+    p.println('if (tid == 0)')
+    p.do_scope()
+    for node in lay.loaded_inputs:
+      p.println('soda::tma_prefetch_desc(&a.in_map[%d]);' % node.input_index)
+    p.println('for (int n = 0; n < %d; ++n) soda::mbar_init(&bars[n], 1);' %
+              self.DIN)
+    p.println('soda::mbar_fence_init();')
+    p.un_scope()
+    p.println('__syncthreads();')
+    p.println('if (tid == 0)')
+    p.do_scope()
+    p.println('for (int rel = 0; rel < %d && rel < steps; ++rel)' % self.P)
+    p.do_scope()
+    self.tma_issue('rel')
+    p.un_scope()
+    p.un_scope()
+    p.un_scope()
+    p.println('else')
+    p.do_scope()
+    p.do_scope()
+    self.plain_load('0')
+    p.un_scope()
+    p.println('__syncthreads();')
+    p.un_scope()
+    p.println()
+
+  # ---- one step ---------------------------------------------------------------
+  def emit_step(self, phase):
+    p, sched, lay, V = self.p, self.sched, self.lay, self.V
+    if self.flat:
+      # request the row `prefetch` steps ahead; it lands in the slot that
+      # step ii + prefetch reads as age 0
+      p.do_scope()
+      self.emit_row_load(phase, 'ii + %d' % self.P, -self.P)
+      p.un_scope()
+    elif lay.loaded_inputs:
+      p.println('if (kTma)')
+      p.do_scope()
+      p.println('if (tid == 0 && ii + %d < steps)' % self.P)
+      p.do_scope()
+      self.tma_issue('ii + %d' % self.P)
+      p.un_scope()
+      p.println('soda::mbar_wait(&bars[ii & %d], (ii >> %d) & 1);' % (
+          self.DIN - 1, _log2(self.DIN)))
+      p.un_scope()
+      for node in lay.loaded_inputs:
+        if node.hist_oldest is None:
+          continue
+        p.println('#pragma unroll')
+        p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
+        p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %s * %d + pos[j]);'
+                  % (node.c_type, V, self.hist(node, phase, 0), node.ident,
+                     self.ring_slot(node, 0), self.PLANE))
+    self.shuffled = {}     # (node index, age, element) -> variable, this step
+    for node in sched.stage_nodes:
+      self.emit_stage(node, phase)
+    if not self.flat:
+      if lay.loaded_inputs:
+        p.println('if (!kTma && ii + 1 < steps)')
+        p.do_scope()
+        self.plain_load('ii + 1')
+        p.un_scope()
+      p.println('__syncthreads();')
+
+  def emit_stage(self, node, phase):
+    p, sched, lay, s, V = self.p, self.sched, self.lay, self.s, self.V
+    stage = node.stage
+    p.println('// %s: plane ii - %d' % (node.ident, node.delay))
+    # shuffle variables live at step scope so later stages can reuse them
+    reg_loads = [(parent, off) for parent, off in node.loads
+                 if not sched.via_smem(off)]
+    fresh = []
+    for parent, off in reg_loads:
+      age = node.delay - off[s]
+      for c in sorted({k + off[0] for k in range(V)}):
+        if 0 <= c < V:
+          continue
+        key = (parent.index, age, c)
+        if key in self.shuffled:
+          continue
+        var = 'x_%s_a%s_%s' % (parent.ident, str(age).replace('-', 'm'),
+                               ('m%d' % -c) if c < 0 else ('p%d' % c))
+        self.shuffled[key] = var
+        fresh.append((parent, age, c, var))
+        p.println('%s %s[%d];' % (parent.c_type, var, self.VPT))
+    p.do_scope()
+    if node.output_index is not None:
+      p.println('const int row = base + ii - %d;' % node.delay)
+      p.println('const bool row_mine = row >= r0 && row < r1;')
+      p.println('const bool row_ok = row >= a.valid_lo[%d] && row < '
+                'a.valid_hi[%d];' % (s, s))
+    p.println('#pragma unroll')
+    p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
+    p.do_scope()
+    for parent, age, c, var in fresh:
+      lanes, elem = divmod(c, V)      # c < 0: lanes < 0 (from the left)
+      src = '%s[j][%d]' % (self.hist(parent, phase, age), elem)
+      if lanes < 0:
+        p.println('%s[j] = soda::shfl_up<%s>(%s, %d);' % (
+            var, parent.c_type, src, -lanes))
+      else:
+        p.println('%s[j] = soda::shfl_down<%s>(%s, %d);' % (
+            var, parent.c_type, src, lanes))
+
+    # operands read through shared memory: one window per (parent, offsets in
+    # dims 1..), as in kernel.py
+    groups = collections.OrderedDict()
+    parent_of = {}
+    for parent, off in node.loads:
+      if not sched.via_smem(off):
+        continue
+      key = (parent.index, off[1:])
+      groups.setdefault(key, set()).add(off[0])
+      parent_of[parent.index] = parent
+    window_of = {}
+    for g, ((pindex, rest), dxs) in enumerate(groups.items()):
+      parent = parent_of[pindex]
+      xlo, xhi = min(dxs), max(dxs)
+      used = sorted({k + dx for dx in dxs for k in range(V)})
+      inplane = sum(rest[d - 1] * sched.plane_pitch(d) for d in range(1, s))
+      age = node.delay - rest[s - 1]
+      p.println('const %s* const s%d = ring_%s + %s * %d + pos[j] + (%d);' % (
+          parent.c_type, g, parent.ident, self.ring_slot(parent, age),
+          self.PLANE, inplane))
+      p.println('%s w%d[%d];' % (parent.c_type, g, V + xhi - xlo))
+      inside = [c for c in used if 0 <= c < V]
+      if len(inside) >= 2 and xlo <= 0 <= xhi:
+        p.println('soda::ld_pack<%s, %d>(w%d + %d, s%d);' % (
+            parent.c_type, V, g, -xlo, g))
+        outside = [c for c in used if not 0 <= c < V]
+      else:
+        outside = used
+      for c in outside:
+        p.println('w%d[%d] = s%d[%d];' % (g, c - xlo, g, c))
+      window_of[(pindex, rest)] = (g, xlo)
+
+    resolved = dict(zip(
+        [l for l in stage.loads if l.parent not in sched.program.params],
+        node.loads))
+
+    def ref_code(load, k):
+      parent, off = resolved[load]
+      if sched.via_smem(off):
+        g, xlo = window_of[(parent.index, off[1:])]
+        return 'w%d[%d]' % (g, k + off[0] - xlo)
+      age = node.delay - off[s]
+      c = k + off[0]
+      if 0 <= c < V:
+        return '%s[j][%d]' % (self.hist(parent, phase, age), c)
+      return '%s[j]' % self.shuffled[(parent.index, age, c)]
+
+    keeps = node.hist_oldest is not None
+    target = ('%s[j]' % self.hist(node, phase, node.delay)) if keeps else 'r'
+    if not keeps:
+      p.println('%s r[%d];' % (node.c_type, V))
+    for k in range(V):
+      lets, expr = _render(stage, ref_code, k)
+      if lets:
+        p.do_scope()
+        for let in lets:
+          p.println(let)
+      p.println('%s[%d] = %s;' % (target, k, expr))
+      if lets:
+        p.un_scope()
+    if node.index in lay.ring_offset:
+      p.println('soda::st_pack<%s, %d>(ring_%s + %s * %d + pos[j], %s);' % (
+          node.c_type, V, node.ident, self.ring_slot(node, node.delay),
+          self.PLANE, target))
+    if node.output_index is not None:
+      full = (1 << V) - 1
+      p.println('if (row_mine && own[j])')
+      p.do_scope()
+      p.println('%s* const dst = static_cast<%s*>(a.out_ptr[%d]) + row * '
+                'a.stride[%d] + goff[j];' % (node.c_type, node.c_type,
+                                             node.output_index, s))
+      p.println('%s o[%d];' % (node.c_type, V))
+      p.println('const unsigned keep = row_ok ? val[j] : 0u;')
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      p.println('  o[k] = ((keep >> k) & 1u) ? %s[k] : %s(0);' % (
+          target, node.c_type))
+      p.println('if (own[j] == %du && a.vec_store)' % full)
+      p.do_scope()
+      p.println('soda::st_pack_global<%s, %d>(dst, o);' % (node.c_type, V))
+      p.un_scope()
+      p.println('else')
+      p.do_scope()
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      p.println('  if ((own[j] >> k) & 1u) dst[k] = o[k];')
+      p.un_scope()
+      p.un_scope()
+    p.un_scope()
+    p.un_scope()
+
+
+def emit_kernel(p, sched):
+  """Write the kernel for ``sched`` through Printer ``p``; returns its Layout."""
+  return _Emitter(p, sched).emit()

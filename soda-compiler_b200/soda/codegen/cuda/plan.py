@@ -280,6 +280,9 @@ class Schedule:
     prefetch: input planes requested ahead of the one being consumed.
   """
 
+  style = 'ring'
+  tiles_per_block = 1
+
   def __init__(self, program, depth, tile, vec, threads, prefetch=2):
     self.program = program
     self.depth = depth
@@ -303,9 +306,10 @@ class Schedule:
     if self.tile[0] % vec:
       raise util.SemanticError('tile width must be a multiple of vec')
     self.plane_vecs = self.plane_elems // vec
-    if self.plane_vecs % threads:
+    tile_threads = threads // self.tiles_per_block
+    if self.plane_vecs % tile_threads:
       raise util.SemanticError('threads must divide the vectors per plane')
-    self.vecs_per_thread = self.plane_vecs // threads
+    self.vecs_per_thread = self.plane_vecs // tile_threads
     self._build_nodes()
     self._assign_delays()
     self._size_rings()
@@ -422,6 +426,107 @@ class Schedule:
     for node in self.nodes:
       lines.append('  %-16s delay %3d ring %2d %s' % (
           node.ident, node.delay, node.ring_depth,
+          '-> out[%d]' % node.output_index
+          if node.output_index is not None else ''))
+    return '\n'.join(lines)
+
+
+# --- the register-streaming schedule -----------------------------------------
+
+class RegSchedule(Schedule):
+  """``depth`` iterations fused into one register-streaming kernel.
+
+  Same streamed/tiled split as ``Schedule``, but a tensor of the fused chain
+  is no longer a shared-memory ring by default.  One warp spans the tile in
+  dimension 0 (``tile[0] == 32 * vec``) and every thread walks the streamed
+  dimension with its own ``vec`` cells, so
+
+  * a load at offsets (dx, 0, .., dz) is served from the thread's **register
+    history** of the parent (the last few streamed planes of its own cells);
+    ``dx != 0`` takes the missing cells from the neighbouring lanes with warp
+    shuffles — this is the whole story for 2-D programs, which use no shared
+    memory and no block barrier at all: a block is ``warps`` independent
+    strips, inputs come straight from HBM with 128-bit loads issued
+    ``prefetch`` rows ahead into the history registers;
+  * only a load with an in-plane offset in a dimension other than 0 (3-D:
+    dy != 0) goes through a **shared-memory plane ring** of the parent, which
+    the producing stage writes next to its registers; such a parent must have
+    been written in an earlier step (one block barrier per step), a register
+    parent may be produced in the same step, so the pipeline is as short as
+    the data dependences allow.  Inputs of 3-D programs arrive by TMA in a
+    plane ring as before and are copied to the history once per step.
+
+  Register histories are addressed statically: the streamed loop is unrolled
+  ``period`` times and the row of age k (computed k steps ago) of a node
+  lives in slot ``(phase - k) mod period``.
+  """
+
+  style = 'reg'
+
+  def __init__(self, program, depth, vec, warps, tile_rest=(), prefetch=2):
+    self.warps = warps
+    self.tiles_per_block = warps if program.dim == 2 else 1
+    self.input_in_smem = program.dim > 2
+    super().__init__(program, depth, (32 * vec,) + tuple(tile_rest), vec,
+                     32 * warps, prefetch)
+
+  def via_smem(self, off):
+    """Does a load at offset ``off`` need the parent's shared plane?"""
+    return any(off[1:self.sdim])
+
+  def _assign_delays(self):
+    s = self.sdim
+    for node in self.stage_nodes:
+      needs = []
+      for parent, off in node.loads:
+        lag = 1 if self.via_smem(off) and not parent.is_input else 0
+        needs.append(parent.delay + lag + off[s])
+      node.delay = max(needs) if needs else 0
+    self.out_delay = max(node.delay for node in self.outputs)
+
+  def _size_rings(self):
+    s = self.sdim
+    spans = [1]
+    for node in self.nodes:
+      reg_ages = [c.delay - off[s] for c, off in node.consumers
+                  if not self.via_smem(off)]
+      smem_ages = [c.delay - off[s] for c, off in node.consumers
+                   if self.via_smem(off)]
+      # registers hold the rows of age node.delay .. hist_oldest
+      node.hist_oldest = max(reg_ages) if reg_ages else None
+      node.hist_newest = node.delay
+      if node.is_input and not self.input_in_smem and reg_ages:
+        node.hist_newest = -self.prefetch      # rows in flight from HBM
+      if node.is_input and self.input_in_smem:
+        node.ring_depth = (_pow2(max(smem_ages + [0]) + self.prefetch + 1)
+                           if node.consumers else 0)
+      elif smem_ages:
+        node.ring_depth = _pow2(max(smem_ages) - node.delay + 1)
+      else:
+        node.ring_depth = 0
+      if reg_ages:
+        spans.append(node.hist_oldest - node.hist_newest + 1)
+    self.period = max(spans)
+
+  def _measure_halos(self):
+    super()._measure_halos()
+    reach = [abs(self.plane_offset(off)) for node in self.stage_nodes
+             for _, off in node.loads if self.via_smem(off)]
+    self.guard_elems = max(reach) if reach else 0
+
+  def describe(self):
+    lines = ['register-streaming schedule %s: depth %d, tile %s x %d/block, '
+             'vec %d, %d threads, period %d, own %s, halo -%s +%s, lead %d, '
+             'out delay %d' % (
+                 self.program.app_name, self.depth, self.tile,
+                 self.tiles_per_block, self.vec, self.threads, self.period,
+                 self.own, self.tile_halo_lo, self.tile_halo_hi, self.lead,
+                 self.out_delay)]
+    for node in self.nodes:
+      lines.append('  %-16s delay %3d regs %s ring %2d %s' % (
+          node.ident, node.delay,
+          'ages %d..%d' % (node.hist_newest, node.hist_oldest)
+          if node.hist_oldest is not None else '-', node.ring_depth,
           '-> out[%d]' % node.output_index
           if node.output_index is not None else ''))
     return '\n'.join(lines)

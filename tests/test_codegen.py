@@ -29,9 +29,17 @@ def test_kernel_and_host_to_files_and_stdout(tmp_path):
          'const char* xclbin)' in done.stdout
   text = kernel.read_text()
   assert '__global__ void __launch_bounds__' in text
+  # 2-D programs stream through registers: 128-bit loads, warp shuffles
+  assert 'soda::ld_stream<uint16_t, 8>(' in text and 'soda::shfl_down<' in text
+  # the reference-lowered expressions, operands mapped to register histories
+  assert '/ 3)' in text and 'r[0] = (' in text
+  ring = tmp_path / 'ring.cu'
+  done = sodac(common.bench_path('blur'), '--cuda-kernel', str(ring),
+               '--cuda-style', 'ring')
+  assert done.returncode == 0, done.stderr
+  text = ring.read_text()
   assert 'soda::tma_load(' in text and 'soda::mbar_wait(' in text
-  # the reference-lowered expressions, operands mapped to register windows
-  assert '/ 3)' in text and text.count('r[k] = (') == 2
+  assert text.count('r[k] = (') == 2
   assert 'int blur(' in host.read_text()
   assert 'soda_cuda_run' in host.read_text()
 

@@ -1,0 +1,64 @@
+#!/usr/bin/env python3
+"""Compile, here (no GPU needed), every library the GPU tests and benchmarks
+load, so that GPU-box time is not spent in nvcc.  Builds are cached in-tree
+under soda-compiler_b200/_build/ and travel with the repository snapshot.
+
+  python tools/prebuild.py [--clean] [case ...]     case = quick_bench syntax
+"""
+import concurrent.futures
+import os
+import shutil
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for sub in ('', 'tests', 'oracle', 'soda-compiler_b200', 'tools'):
+  sys.path.insert(0, os.path.join(ROOT, sub))
+
+from soda import core, cuda as soda_cuda          # noqa: E402
+from soda.codegen import cuda as codegen          # noqa: E402
+
+
+def build(job):
+  name, iterate, options = job
+  stencil = core.Stencil.from_file(
+      os.path.join(ROOT, 'benchmarks', name + '.soda'), iterate=iterate)
+  return soda_cuda.build(stencil, options=codegen.Options(**options))
+
+
+def main():
+  args = sys.argv[1:]
+  if '--clean' in args:
+    args.remove('--clean')
+    shutil.rmtree(soda_cuda.DEFAULT_BUILD_DIR, ignore_errors=True)
+  jobs = []
+  if args:
+    import quick_bench
+    for text in args:
+      name, iterate, _, options = quick_bench.parse_case(text)
+      options.pop('e2e', None)
+      jobs.append((name, iterate, options))
+  else:
+    import test_parity_gpu
+    import test_slab_gpu
+    import __graft_entry__ as entry
+    for name, iterate, _, options in test_parity_gpu.CASES:
+      jobs.append((name, iterate, options))
+    for name, iterate, _ in test_parity_gpu.REF_CASES:
+      jobs.append((name, iterate, {}))
+    del test_slab_gpu
+    jobs += [('jacobi2d', 16, {'depth': 4}), ('jacobi2d', 7, {'depth': 4}),
+             ('heat3d', 4, {'depth': 2}), ('denoise2d', 1, {})]
+    jobs += [(n, None, {}) for n in entry.BENCHMARKS]
+    jobs += [(n, it, {}) for n, it in entry.EXTRA_BUILDS]
+  unique = []
+  for job in jobs:
+    key = (job[0], job[1], sorted(job[2].items()))
+    if key not in [(j[0], j[1], sorted(j[2].items())) for j in unique]:
+      unique.append(job)
+  with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+    for job, path in zip(unique, pool.map(build, unique)):
+      print('%-40s %s' % (job, os.path.relpath(path, ROOT)))
+
+
+if __name__ == '__main__':
+  main()
