@@ -32,6 +32,7 @@ SUPPORTED_TYPES = {
     'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32', 'int64',
     'float', 'float32', 'double', 'float64'}
 SMEM_LIMIT = 227 * 1024
+REG_HISTORY_BUDGET = 80   # registers per thread held across steps (2-D)
 
 
 def add_arguments(parser):
@@ -60,6 +61,14 @@ def add_arguments(parser):
       '--cuda-prefetch', type=int, dest='cuda_prefetch', metavar='N',
       help='input planes requested ahead of the one being consumed')
   parser.add_argument(
+      '--cuda-min-blocks', type=int, dest='cuda_min_blocks', metavar='N',
+      help='resident blocks per SM the kernel is compiled for (caps its '
+      'registers)')
+  parser.add_argument(
+      '--cuda-paired', type=int, dest='cuda_paired', metavar='0|1',
+      help='evaluate fused iterations k and k + depth/2 together on packed '
+      'f32x2 arithmetic (default: whenever the program allows it)')
+  parser.add_argument(
       '--cuda-style', type=str, dest='cuda_style', choices=['reg', 'ring'],
       help='kernel family: `reg` keeps the streamed window of every tensor '
       'in registers and shares dimension-0 neighbours by warp shuffle '
@@ -70,9 +79,11 @@ class Options:
   """Tuning knobs of the backend; None means "choose for me"."""
 
   def __init__(self, depth=None, tile=None, threads=None, vec=None,
-               prefetch=None, style=None):
+               prefetch=None, style=None, paired=None, min_blocks=None):
     self.depth, self.tile, self.threads = depth, tile, threads
     self.vec, self.prefetch, self.style = vec, prefetch, style
+    self.paired = None if paired is None else bool(paired)
+    self.min_blocks = min_blocks
 
   @classmethod
   def from_args(cls, args):
@@ -81,12 +92,15 @@ class Options:
                threads=getattr(args, 'cuda_threads', None),
                vec=getattr(args, 'cuda_vec', None),
                prefetch=getattr(args, 'cuda_prefetch', None),
-               style=getattr(args, 'cuda_style', None))
+               style=getattr(args, 'cuda_style', None),
+               paired=getattr(args, 'cuda_paired', None),
+               min_blocks=getattr(args, 'cuda_min_blocks', None))
 
   def key(self):
-    return 'd%s_t%s_n%s_v%s_p%s_%s' % (
+    return 'd%s_t%s_n%s_v%s_p%s_%s_%s_%s' % (
         self.depth, 'x'.join(map(str, self.tile)) if self.tile else None,
-        self.threads, self.vec, self.prefetch, self.style)
+        self.threads, self.vec, self.prefetch, self.style, self.paired,
+        self.min_blocks)
 
 
 def check_supported(program):
@@ -135,7 +149,12 @@ def _make_reg_schedule(program, depth, options, limit):
     warps = (options.threads or 128) // 32
     prefetch = options.prefetch if options.prefetch is not None else (
         4 if depth <= 2 else 3 if depth <= 4 else 2)
-    return plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch)
+    paired = (options.paired if options.paired is not None else
+              plan_mod.pairing_obstacle(program, depth) is None)
+    sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
+                                 paired=paired)
+    sched.min_blocks = options.min_blocks or default_min_blocks(sched)
+    return sched
   if options.tile:
     if options.tile[0] != 32 * vec:
       raise util.SemanticError('register-streaming tiles are 32 x vec = %d '
@@ -207,6 +226,29 @@ def make_schedule(program, depth, options, limit=SMEM_LIMIT):
   raise problem
 
 
+def default_min_blocks(sched):
+  """Resident blocks per SM to compile a 2-D register kernel for: enough
+  registers for the histories plus working set, as many warps as that
+  leaves."""
+  need = history_registers(sched) + 40
+  for node in sched.inputs:        # rows in flight
+    words = -(-sched.vec * node.elem_size // 4)
+    need += ((sched.prefetch + 1) * words if getattr(node, 'staged', False)
+             else sched.prefetch * max(words, sched.vec))
+  blocks = 65536 // (sched.threads * max(need, 32))
+  return max(1, min(blocks, 2048 // sched.threads, 16))
+
+
+def history_registers(sched):
+  """Registers a thread of a register-streaming kernel keeps across steps."""
+  total = 0
+  for node in sched.nodes:
+    if node.hist_oldest is not None:
+      total += (node.hist_oldest - node.delay) * sched.vec * \
+          sched.vecs_per_thread * (2 if sched.paired else 1)
+  return total
+
+
 def make_schedules(program, options=None):
   """The kernel variants to compile: the main temporal depth and, when it does
   not divide ``iterate``, the depth of the remainder."""
@@ -218,7 +260,16 @@ def make_schedules(program, options=None):
   elif not program.feedback or iterate == 1:
     main = 1
   elif options.style in (None, 'reg') and program.dim == 2:
-    main = min(iterate, 4)
+    # as deep as the register file carries comfortably: every fused level
+    # keeps (rows of history - 1) x vec values live across steps
+    main = 1
+    for depth in (2, 4, 8, 16):
+      if depth > iterate:
+        break
+      sched = make_schedule(program, depth, options)
+      if sched.style != 'reg' or history_registers(sched) > REG_HISTORY_BUDGET:
+        break
+      main = depth
   else:
     main = 1
     for depth in (2, 4, 8, 16):

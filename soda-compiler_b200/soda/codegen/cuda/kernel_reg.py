@@ -120,6 +120,15 @@ class _Emitter:
     """Register array holding the row of ``node`` that is ``age`` steps old."""
     return 'h_%s_%d' % (node.ident, (phase - age) % self.U)
 
+  def raw(self, node, phase, age):
+    """Paired 2-D kernels: staging slot of an input row still in flight."""
+    return 'g_%s_%d' % (node.ident, (phase - age) % self.U)
+
+  def ctype(self, node):
+    """Type of a cell of ``node`` in registers: a pair of float32 (iteration
+    k, iteration k + depth/2) when the schedule pairs iterations."""
+    return 'soda::f32x2' if self.sched.paired else node.c_type
+
   def ring_slot(self, node, age):
     depth = self.lay.ring_depth[node.index]
     return '((ii - (%d)) & %d)' % (age, depth - 1)
@@ -130,7 +139,8 @@ class _Emitter:
     name = kernel_name(sched)
     p.println('// %s' % sched.describe().replace('\n', '\n// '))
     p.println('template <bool kTma>')
-    p.println('__global__ void __launch_bounds__(%d) %s(' % (self.NT, name))
+    p.println('__global__ void __launch_bounds__(%d, %d) %s(' % (
+        self.NT, sched.min_blocks, name))
     p.println('    const __grid_constant__ soda::StreamArgs a)')
     p.do_scope()
     if lay.total:
@@ -154,6 +164,7 @@ class _Emitter:
       self.emit_flat_prologue()
     else:
       self.emit_tma_prologue()
+    self.emit_output_windows()
     p.println('for (int i = 0; i < steps; i += %d)' % self.U)
     p.do_scope()
     for phase in range(self.U):
@@ -202,6 +213,8 @@ class _Emitter:
     p.println('int pos[%d];' % VPT)
     p.println('long long goff[%d];' % VPT)
     p.println('unsigned own[%d], val[%d];' % (VPT, VPT))
+    p.println('bool fast[%d];   // whole vector owned and valid: one 128-bit '
+              'store' % VPT)
     p.println('bool xin[%d];   // the vector lies inside the grid in the tiled '
               'dims' % VPT)
     p.println('int gx[%d];' % VPT)
@@ -249,7 +262,35 @@ class _Emitter:
     p.un_scope()
     p.println('own[j] = m;')
     p.println('val[j] = v;')
+    p.println('fast[j] = m == %du && v == %du && a.vec_store;' % (
+        (1 << V) - 1, (1 << V) - 1))
     p.un_scope()
+    p.println()
+
+  def out_lag(self, node):
+    """An output row leaves ``out_lag`` steps after its input row arrived."""
+    return node.delay + (self.sched.pair_lag if self.sched.paired else 0)
+
+  def emit_output_windows(self):
+    """Per output: the steps whose row this block stores ([mine_lo, mine_hi))
+    and, inside, the steps whose row lies in the valid region ([ok_lo, ok_lo +
+    ok_n)); plus the output pointers, which walk down the rows with the steps."""
+    p, sched, s = self.p, self.sched, self.s
+    for node in sched.outputs:
+      n, lag = node.output_index, self.out_lag(node)
+      p.println('const int mine_lo%d = %d, mine_hi%d = (r1 - r0) + %d;' % (
+          n, sched.lead + lag, n, sched.lead + lag))
+      p.println('const int ok_lo%d = max(mine_lo%d, a.valid_lo[%d] - base + '
+                '%d);' % (n, n, s, lag))
+      p.println('const unsigned ok_n%d = static_cast<unsigned>(max(0, min('
+                'mine_hi%d, a.valid_hi[%d] - base + %d) - ok_lo%d));' % (
+                    n, n, s, lag, n))
+      p.println('%s* op%d[%d];   // row of step 0 (dereferenced only inside '
+                'the window)' % (node.c_type, n, self.VPT))
+      p.println('#pragma unroll')
+      p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
+      p.println('  op%d[j] = static_cast<%s*>(a.out_ptr[%d]) + (base - %d) * '
+                'a.stride[%d] + goff[j];' % (n, node.c_type, n, lag, s))
     p.println()
 
   def emit_histories(self):
@@ -261,40 +302,76 @@ class _Emitter:
         continue
       for slot in range(self.U):
         p.println('%s h_%s_%d[%d][%d] = {};' % (
-            node.c_type, node.ident, slot, self.VPT, self.V))
+            self.ctype(node), node.ident, slot, self.VPT, self.V))
+      if node.staged:
+        for slot in range(self.U):
+          p.println('soda::Raw<%s, %d> g_%s_%d[%d] = {};   // rows in flight' %
+                    (node.c_type, self.V, node.ident, slot, self.VPT))
+      if sched.paired and node.is_input:
+        p.println('%s fb_%s[%d][%d] = {};   // newest output row of lane A, '
+                  'input of lane B' % (node.c_type, node.ident, self.VPT,
+                                       self.V))
     p.println()
 
   # ---- 2-D input path: straight from HBM into the history --------------------
   def emit_row_load(self, phase, rel_code, age):
-    """Fetch row ``base + rel`` of every input into the slot of ``age``."""
+    """Fetch row ``base + rel`` of every input into the slot of ``age``; the
+    per-input pointers ``lp<k>`` walk down the rows with the calls.  Rows and
+    columns outside the grid read as 0 (a conditional load that kept the old
+    value instead would keep every dead slot alive in a register)."""
     p, sched, V = self.p, self.sched, self.V
-    p.println('const int lrow = base + (%s);' % rel_code)
-    p.println('const bool lrow_in = lrow >= 0 && lrow < a.dims[%d];' % self.s)
+    p.println('const bool lrow_in = static_cast<unsigned>(base + (%s)) < '
+              'static_cast<unsigned>(a.dims[%d]);' % (rel_code, self.s))
     for node in sched.inputs:
       if node.hist_oldest is None:
         continue
+      k = node.input_index
+      if node.staged:
+        dst = '%s[0]' % self.raw(node, phase, age)
+        p.println('if (kTma)')
+        p.do_scope()
+        # zero first, then the conditional load: the other order parks the
+        # warp on the load's scoreboard (write-after-write on its registers)
+        p.println('soda::raw_zero<%s, %d>(%s);' % (node.c_type, V, dst))
+        p.println('if (lrow_in && xin[0]) soda::ld_stream_raw<%s, %d>(%s, '
+                  'lp%d);' % (node.c_type, V, dst, k))
+        p.un_scope()
+        p.println('else')
+        p.do_scope()
+        p.println('%s t[%d];' % (node.c_type, V))
+        p.println('#pragma unroll')
+        p.println('for (int k = 0; k < %d; ++k)' % V)
+        p.println('  t[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
+                  'a.dims[0]) ? lp%d[k] : %s(0);' % (k, node.c_type))
+        p.println('soda::raw_pack<%s, %d>(%s, t);' % (node.c_type, V, dst))
+        p.un_scope()
+        p.println('lp%d += a.stride[%d];' % (k, self.s))
+        continue
       dst = '%s[0]' % self.hist(node, phase, age)
-      p.println('const %s* const src%d = static_cast<const %s*>('
-                'a.in_ptr[%d]) + lrow * a.stride[%d] + goff[0];' % (
-                    node.c_type, node.input_index, node.c_type,
-                    node.input_index, self.s))
       p.println('if (kTma)')
       p.do_scope()
-      p.println('if (lrow_in && xin[0]) soda::ld_stream<%s, %d>(%s, src%d);' % (
-          node.c_type, V, dst, node.input_index))
-      p.println('else soda::fill_zero<%s, %d>(%s);' % (node.c_type, V, dst))
+      p.println('soda::fill_zero<%s, %d>(%s);' % (node.c_type, V, dst))
+      p.println('if (lrow_in && xin[0]) soda::ld_stream<%s, %d>(%s, lp%d);' % (
+          node.c_type, V, dst, k))
       p.un_scope()
       p.println('else')
       p.do_scope()
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)
       p.println('  %s[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
-                'a.dims[0]) ? src%d[k] : %s(0);' % (
-                    dst, node.input_index, node.c_type))
+                'a.dims[0]) ? lp%d[k] : %s(0);' % (dst, k, node.c_type))
       p.un_scope()
+      p.println('lp%d += a.stride[%d];' % (k, self.s))
 
   def emit_flat_prologue(self):
     p = self.p
+    for node in self.sched.inputs:
+      if node.hist_oldest is None:
+        continue
+      p.println('const %s* lp%d = static_cast<const %s*>(a.in_ptr[%d]) + '
+                'base * a.stride[%d] + goff[0];   // next row to fetch' % (
+                    node.c_type, node.input_index, node.c_type,
+                    node.input_index, self.s))
     p.println('// rows 0 .. %d of this chunk are in flight before the loop '
               'starts' % (self.P - 1))
     for rel in range(self.P):
@@ -390,6 +467,22 @@ class _Emitter:
       p.do_scope()
       self.emit_row_load(phase, 'ii + %d' % self.P, -self.P)
       p.un_scope()
+      # the row that arrived for this step leaves the staging ring: sub-word
+      # cells are unpacked, paired kernels join it with lane B's input row
+      for node in sched.inputs:
+        if node.hist_oldest is None or not node.staged:
+          continue
+        p.println('#pragma unroll')
+        p.println('for (int k = 0; k < %d; ++k)' % V)
+        if sched.paired:
+          p.println('  %s[0][k] = soda::make_f32x2(soda::raw_get<%s, %d>('
+                    '%s[0], k), fb_%s[0][k]);' % (
+                        self.hist(node, phase, 0), node.c_type, V,
+                        self.raw(node, phase, 0), node.ident))
+        else:
+          p.println('  %s[0][k] = soda::raw_get<%s, %d>(%s[0], k);' % (
+              self.hist(node, phase, 0), node.c_type, V,
+              self.raw(node, phase, 0)))
     elif lay.loaded_inputs:
       p.println('if (kTma)')
       p.do_scope()
@@ -439,13 +532,14 @@ class _Emitter:
                                ('m%d' % -c) if c < 0 else ('p%d' % c))
         self.shuffled[key] = var
         fresh.append((parent, age, c, var))
-        p.println('%s %s[%d];' % (parent.c_type, var, self.VPT))
+        p.println('%s %s[%d];' % (self.ctype(parent), var, self.VPT))
     p.do_scope()
     if node.output_index is not None:
-      p.println('const int row = base + ii - %d;' % node.delay)
-      p.println('const bool row_mine = row >= r0 && row < r1;')
-      p.println('const bool row_ok = row >= a.valid_lo[%d] && row < '
-                'a.valid_hi[%d];' % (s, s))
+      n = node.output_index
+      p.println('const bool row_ok = static_cast<unsigned>(ii - ok_lo%d) < '
+                'ok_n%d;' % (n, n))
+      p.println('const bool row_mine = ii >= mine_lo%d && ii < mine_hi%d;' % (
+          n, n))
     p.println('#pragma unroll')
     p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
     p.do_scope()
@@ -454,10 +548,10 @@ class _Emitter:
       src = '%s[j][%d]' % (self.hist(parent, phase, age), elem)
       if lanes < 0:
         p.println('%s[j] = soda::shfl_up<%s>(%s, %d);' % (
-            var, parent.c_type, src, -lanes))
+            var, self.ctype(parent), src, -lanes))
       else:
         p.println('%s[j] = soda::shfl_down<%s>(%s, %d);' % (
-            var, parent.c_type, src, lanes))
+            var, self.ctype(parent), src, lanes))
 
     # operands read through shared memory: one window per (parent, offsets in
     # dims 1..), as in kernel.py
@@ -509,7 +603,7 @@ class _Emitter:
     keeps = node.hist_oldest is not None
     target = ('%s[j]' % self.hist(node, phase, node.delay)) if keeps else 'r'
     if not keeps:
-      p.println('%s r[%d];' % (node.c_type, V))
+      p.println('%s r[%d];' % (self.ctype(node), V))
     for k in range(V):
       lets, expr = _render(stage, ref_code, k)
       if lets:
@@ -523,30 +617,47 @@ class _Emitter:
       p.println('soda::st_pack<%s, %d>(ring_%s + %s * %d + pos[j], %s);' % (
           node.c_type, V, node.ident, self.ring_slot(node, node.delay),
           self.PLANE, target))
-    if node.output_index is not None:
-      full = (1 << V) - 1
-      p.println('if (row_mine && own[j])')
-      p.do_scope()
-      p.println('%s* const dst = static_cast<%s*>(a.out_ptr[%d]) + row * '
-                'a.stride[%d] + goff[j];' % (node.c_type, node.c_type,
-                                             node.output_index, s))
-      p.println('%s o[%d];' % (node.c_type, V))
-      p.println('const unsigned keep = row_ok ? val[j] : 0u;')
+    if node.output_index is not None and sched.paired:
+      # lane A's result (iteration depth/2 - 1) feeds lane B one step later
+      feeds = sched.inputs[node.output_index]
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)
-      p.println('  o[k] = ((keep >> k) & 1u) ? %s[k] : %s(0);' % (
-          target, node.c_type))
-      p.println('if (own[j] == %du && a.vec_store)' % full)
+      p.println('  fb_%s[j][k] = %s[k].v.x;' % (feeds.ident, target))
+    if node.output_index is not None:
+      n = node.output_index
+      half = '.v.y' if sched.paired else ''
+      p.println('if (row_ok && fast[j])')
       p.do_scope()
-      p.println('soda::st_pack_global<%s, %d>(dst, o);' % (node.c_type, V))
+      p.println('%s o[%d];' % (node.c_type, V))
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k) o[k] = %s[k]%s;' % (
+          V, target, half))
+      p.println('soda::st_pack_global<%s, %d>(op%d[j], o);' % (
+          node.c_type, V, n))
+      p.un_scope()
+      p.println('else if (row_mine && own[j])')
+      p.do_scope()
+      p.println('// tile or grid edge: cells outside the valid region are '
+                'stored as 0')
+      p.println('const unsigned keep = row_ok ? val[j] : 0u;')
+      p.println('%s o[%d];' % (node.c_type, V))
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      p.println('  o[k] = ((keep >> k) & 1u) ? %s[k]%s : %s(0);' % (
+          target, half, node.c_type))
+      p.println('if (own[j] == %du && a.vec_store)' % ((1 << V) - 1))
+      p.do_scope()
+      p.println('soda::st_pack_global<%s, %d>(op%d[j], o);' % (
+          node.c_type, V, n))
       p.un_scope()
       p.println('else')
       p.do_scope()
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)
-      p.println('  if ((own[j] >> k) & 1u) dst[k] = o[k];')
+      p.println('  if ((own[j] >> k) & 1u) op%d[j][k] = o[k];' % n)
       p.un_scope()
       p.un_scope()
+      p.println('op%d[j] += a.stride[%d];' % (n, s))
     p.un_scope()
     p.un_scope()
 

@@ -282,6 +282,12 @@ class Schedule:
 
   style = 'ring'
   tiles_per_block = 1
+  paired = False
+
+  @property
+  def chain(self):
+    """Iterations chained node by node (half of ``depth`` when paired)."""
+    return self.depth // 2 if self.paired else self.depth
 
   def __init__(self, program, depth, tile, vec, threads, prefetch=2):
     self.program = program
@@ -338,7 +344,7 @@ class Schedule:
       current[name] = node
     self.inputs = list(self.nodes)
     self.stage_nodes = []
-    for it in range(self.depth):
+    for it in range(self.chain):
       for stage in program.stages:
         node = Node(len(self.nodes), stage.name, it, stage, stage.c_type,
                     util.get_width_in_bytes(stage.haoda_type))
@@ -351,7 +357,7 @@ class Schedule:
         self.nodes.append(node)
         self.stage_nodes.append(node)
         current[stage.name] = node
-      if it + 1 < self.depth:
+      if it + 1 < self.chain:
         for name in program.input_names:
           current[name] = current[program.feedback[name]]
     self.outputs = []
@@ -433,6 +439,45 @@ class Schedule:
 
 # --- the register-streaming schedule -----------------------------------------
 
+_PAIR_TOKEN = None
+
+
+def pairing_obstacle(program, depth):
+  """Why ``depth`` fused iterations of ``program`` cannot run two per
+  instruction on packed f32x2 arithmetic (None if they can).
+
+  Pairing evaluates every stage expression on (iteration k, iteration
+  k + depth/2) operand pairs with add/mul/fma.rn.f32x2, which round each half
+  exactly like the scalar instruction.  That covers float32 tensors and
+  expressions built from + - * on tensor cells, float literals with an `f`
+  suffix and integer literals (C++ converts those to float first).
+  """
+  import re
+  global _PAIR_TOKEN
+  if _PAIR_TOKEN is None:
+    _PAIR_TOKEN = re.compile(
+        r'\s+|[-+*()]|(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?[fF]|\d+(?![.\deE])')
+  if depth < 2 or depth % 2:
+    return 'the depth must be even'
+  if not program.feedback:
+    return 'outputs do not pair with inputs'
+  if program.params:
+    return 'param tensors'
+  for name, haoda_type in program.types.items():
+    if haoda_type not in ('float', 'float32'):
+      return '`%s` is %s, not float32' % (name, haoda_type)
+  for stage in program.stages:
+    lets, expr = stage.render(lambda load: '')
+    if lets:
+      return 'let bindings'
+    pos = 0
+    while pos < len(expr):
+      match = _PAIR_TOKEN.match(expr, pos)
+      if not match:
+        return '`%s` uses more than + - * on float32 operands' % stage.name
+      pos = match.end()
+  return None
+
 class RegSchedule(Schedule):
   """``depth`` iterations fused into one register-streaming kernel.
 
@@ -463,10 +508,17 @@ class RegSchedule(Schedule):
 
   style = 'reg'
 
-  def __init__(self, program, depth, vec, warps, tile_rest=(), prefetch=2):
+  def __init__(self, program, depth, vec, warps, tile_rest=(), prefetch=2,
+               paired=False, min_blocks=1):
     self.warps = warps
+    self.min_blocks = min_blocks     # resident blocks per SM to compile for
     self.tiles_per_block = warps if program.dim == 2 else 1
     self.input_in_smem = program.dim > 2
+    self.paired = paired
+    if paired:
+      why = pairing_obstacle(program, depth)
+      if why:
+        raise util.SemanticError('cannot pair iterations: ' + why)
     super().__init__(program, depth, (32 * vec,) + tuple(tile_rest), vec,
                      32 * warps, prefetch)
 
@@ -483,6 +535,14 @@ class RegSchedule(Schedule):
         needs.append(parent.delay + lag + off[s])
       node.delay = max(needs) if needs else 0
     self.out_delay = max(node.delay for node in self.outputs)
+    if self.paired:
+      # lane B (iterations chain .. depth-1) trails lane A by `pair_lag`
+      # steps: it is fed with lane A's newest output row one step later
+      if len({node.delay for node in self.outputs}) != 1:
+        raise util.SemanticError('cannot pair iterations: outputs are '
+                                 'produced at different delays')
+      self.pair_lag = self.out_delay + 1
+      self.out_delay += self.pair_lag
 
   def _size_rings(self):
     s = self.sdim
@@ -495,8 +555,17 @@ class RegSchedule(Schedule):
       # registers hold the rows of age node.delay .. hist_oldest
       node.hist_oldest = max(reg_ages) if reg_ages else None
       node.hist_newest = node.delay
+      node.staged = False
       if node.is_input and not self.input_in_smem and reg_ages:
-        node.hist_newest = -self.prefetch      # rows in flight from HBM
+        if self.paired or node.elem_size < 4:
+          # rows in flight wait in a staging ring as loaded (ages -prefetch
+          # .. 0) and are unpacked — sub-word cells to one register each,
+          # paired kernels: joined with lane B's row — when they turn age 0;
+          # converting on arrival would stall on the load just issued
+          node.staged = True
+          spans.append(self.prefetch + 1)
+        else:
+          node.hist_newest = -self.prefetch    # rows in flight from HBM
       if node.is_input and self.input_in_smem:
         node.ring_depth = (_pow2(max(smem_ages + [0]) + self.prefetch + 1)
                            if node.consumers else 0)
@@ -515,9 +584,11 @@ class RegSchedule(Schedule):
     self.guard_elems = max(reach) if reach else 0
 
   def describe(self):
-    lines = ['register-streaming schedule %s: depth %d, tile %s x %d/block, '
+    lines = ['%sregister-streaming schedule %s: depth %d, tile %s x %d/block, '
              'vec %d, %d threads, period %d, own %s, halo -%s +%s, lead %d, '
              'out delay %d' % (
+                 'paired (f32x2: iterations k and k+%d share an instruction) '
+                 % self.chain if self.paired else '',
                  self.program.app_name, self.depth, self.tile,
                  self.tiles_per_block, self.vec, self.threads, self.period,
                  self.own, self.tile_halo_lo, self.tile_halo_hi, self.lead,

@@ -59,7 +59,7 @@ def _unused():
 
 
 def main():
-  reps = int(os.environ.get('REPS', '5'))
+  reps = int(os.environ.get('REPS', '7'))
   for text in sys.argv[1:]:
     name, iterate, dims, options = parse_case(text)
     e2e = options.pop('e2e', 0)
