@@ -30,7 +30,7 @@ def test_kernel_and_host_to_files_and_stdout(tmp_path):
   text = kernel.read_text()
   assert '__global__ void __launch_bounds__' in text
   # 2-D programs stream through registers: 128-bit loads, warp shuffles
-  assert 'soda::ld_stream<uint16_t, 8>(' in text and 'soda::shfl_down<' in text
+  assert 'soda::ld_stream_raw<uint16_t, 8>(' in text and 'soda::shfl_down<' in text
   # the reference-lowered expressions, operands mapped to register histories
   assert '/ 3)' in text and 'r[0] = (' in text
   ring = tmp_path / 'ring.cu'
