@@ -263,7 +263,7 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
       for (int d = 0; d < prog.dim; ++d) {
         gdim[d] = static_cast<cuuint64_t>(dims[d]);
         estr[d] = 1;
-        box[d] = d == 0 ? kv->box0 : (d < s ? kv->tile[d] : 1);
+        box[d] = d == 0 ? kv->box0 : (d < s ? kv->tile[d] : kv->box_rows);
         if (d > 0)
           gstride[d - 1] =
               static_cast<cuuint64_t>(args.stride[d]) * prog.in_elem[k];

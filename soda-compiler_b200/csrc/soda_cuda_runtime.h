@@ -35,6 +35,7 @@ struct KernelVariant {
   int smem_bytes;
   int box0;                     // TMA box extent along dim 0
   int boxes_per_row;
+  int box_rows;                 // TMA box extent along the streamed dim
   int tiles_per_block;          // 2-D register kernels: strips (warps) per block
   int uses_tma;                 // the first kernel below needs tensor maps
   const void* kernel_tma;       // __global__ void(StreamArgs): TMA / aligned

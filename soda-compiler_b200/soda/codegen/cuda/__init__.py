@@ -61,6 +61,10 @@ def add_arguments(parser):
       '--cuda-prefetch', type=int, dest='cuda_prefetch', metavar='N',
       help='input planes requested ahead of the one being consumed')
   parser.add_argument(
+      '--cuda-groups', type=int, dest='cuda_groups', metavar='N',
+      help='2-D kernels: TMA boxes in the per-warp input queue (4, 8, ..); '
+      'a box holds prefetch / (N - 2) rows')
+  parser.add_argument(
       '--cuda-min-blocks', type=int, dest='cuda_min_blocks', metavar='N',
       help='resident blocks per SM the kernel is compiled for (caps its '
       'registers)')
@@ -79,11 +83,13 @@ class Options:
   """Tuning knobs of the backend; None means "choose for me"."""
 
   def __init__(self, depth=None, tile=None, threads=None, vec=None,
-               prefetch=None, style=None, paired=None, min_blocks=None):
+               prefetch=None, style=None, paired=None, min_blocks=None,
+               groups=None):
     self.depth, self.tile, self.threads = depth, tile, threads
     self.vec, self.prefetch, self.style = vec, prefetch, style
     self.paired = None if paired is None else bool(paired)
     self.min_blocks = min_blocks
+    self.groups = groups
 
   @classmethod
   def from_args(cls, args):
@@ -94,13 +100,14 @@ class Options:
                prefetch=getattr(args, 'cuda_prefetch', None),
                style=getattr(args, 'cuda_style', None),
                paired=getattr(args, 'cuda_paired', None),
-               min_blocks=getattr(args, 'cuda_min_blocks', None))
+               min_blocks=getattr(args, 'cuda_min_blocks', None),
+               groups=getattr(args, 'cuda_groups', None))
 
   def key(self):
-    return 'd%s_t%s_n%s_v%s_p%s_%s_%s_%s' % (
+    return 'd%s_t%s_n%s_v%s_p%s_%s_%s_%s_g%s' % (
         self.depth, 'x'.join(map(str, self.tile)) if self.tile else None,
         self.threads, self.vec, self.prefetch, self.style, self.paired,
-        self.min_blocks)
+        self.min_blocks, self.groups)
 
 
 def check_supported(program):
@@ -147,12 +154,13 @@ def _make_reg_schedule(program, depth, options, limit):
   vec = options.vec or min(default_vec(program), 8)
   if program.dim == 2:
     warps = (options.threads or 128) // 32
-    prefetch = options.prefetch if options.prefetch is not None else (
-        4 if depth <= 2 else 3 if depth <= 4 else 2)
     paired = (options.paired if options.paired is not None else
               plan_mod.pairing_obstacle(program, depth) is None)
+    groups = options.groups or plan_mod.FLAT_GROUPS
+    prefetch = options.prefetch if options.prefetch is not None else (
+        4 * (groups - 2))
     sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
-                                 paired=paired)
+                                 paired=paired, groups=groups)
     sched.min_blocks = options.min_blocks or default_min_blocks(sched)
     return sched
   if options.tile:
@@ -230,13 +238,10 @@ def default_min_blocks(sched):
   """Resident blocks per SM to compile a 2-D register kernel for: enough
   registers for the histories plus working set, as many warps as that
   leaves."""
-  need = history_registers(sched) + 40
-  for node in sched.inputs:        # rows in flight
-    words = -(-sched.vec * node.elem_size // 4)
-    need += ((sched.prefetch + 1) * words if getattr(node, 'staged', False)
-             else sched.prefetch * max(words, sched.vec))
+  need = history_registers(sched) + 64
   blocks = 65536 // (sched.threads * max(need, 32))
-  return max(1, min(blocks, 2048 // sched.threads, 16))
+  smem = kernel_reg_mod.Layout(sched).total + 1024   # + per-block reserve
+  return max(1, min(blocks, 2048 // sched.threads, SMEM_LIMIT // smem, 16))
 
 
 def history_registers(sched):

@@ -11,10 +11,15 @@ reference src/soda/codegen/xilinx/host.py:1093-1117; FPGA counterpart
 src/soda/codegen/xilinx/hls_kernel.py:487-489) is spliced in once per cell of
 the thread's vector.
 
-2-D programs  no shared memory, no barrier.  A block is ``warps`` independent
-              strips of 32 x vec cells; input rows are fetched ``prefetch``
-              rows ahead with 128-bit ``ld.global.nc`` straight into the
-              history registers; outputs leave with 128-bit streaming stores.
+2-D programs  no block barrier.  A block is ``warps`` independent strips of
+              32 x vec cells.  Each warp owns a shared-memory ring of input
+              rows: one elected lane requests row i + prefetch by TMA
+              (cp.async.bulk.tensor.2d, out-of-grid cells arrive as 0) on the
+              slot's mbarrier, every lane takes its cells of row i with one
+              128-bit shared load.  Rows in flight cost no registers, so the
+              queue is as deep as the HBM latency needs.  Outputs leave with
+              128-bit streaming stores.  Shapes TMA cannot describe take
+              element-wise loads one row ahead instead (kTma = false).
 3-D programs  input planes arrive by TMA (cp.async.bulk.tensor + mbarrier) in
               a shared ring as in kernel.py; each thread copies its own cells
               of the newest plane into its history; stages whose results are
@@ -62,6 +67,22 @@ class Layout:
       offset += -(-8 * self.in_depth // 128) * 128
     self.total = offset if self.ring_offset else 0
     self.loaded_inputs = loaded
+    if sched.sdim == 1:
+      # per-warp input queue: `slots` rows of every input that is read, then
+      # one mbarrier per slot
+      self.slots = sched.flat_slots
+      self.box_rows = sched.flat_box
+      self.groups = self.slots // self.box_rows
+      loaded = self.loaded_inputs = [n for n in sched.inputs
+                                     if n.hist_oldest is not None]
+      self.row_bytes = {n.index: sched.tile[0] * n.elem_size for n in loaded}
+      self.queue_offset, offset = {}, 0
+      for node in loaded:
+        self.queue_offset[node.index] = offset
+        offset += -(-self.slots * self.row_bytes[node.index] // 128) * 128
+      self.warp_bytes = offset
+      self.bar_offset = offset * sched.warps
+      self.total = self.bar_offset + -(-8 * self.groups * sched.warps // 128) * 128
     self.plane_bytes = {n.index: sched.plane_elems * n.elem_size
                         for n in loaded}
     self.box0 = sched.tile[0]
@@ -120,10 +141,6 @@ class _Emitter:
     """Register array holding the row of ``node`` that is ``age`` steps old."""
     return 'h_%s_%d' % (node.ident, (phase - age) % self.U)
 
-  def raw(self, node, phase, age):
-    """Paired 2-D kernels: staging slot of an input row still in flight."""
-    return 'g_%s_%d' % (node.ident, (phase - age) % self.U)
-
   def ctype(self, node):
     """Type of a cell of ``node`` in registers: a pair of float32 (iteration
     k, iteration k + depth/2) when the schedule pairs iterations."""
@@ -145,6 +162,15 @@ class _Emitter:
     p.do_scope()
     if lay.total:
       p.println('extern __shared__ __align__(1024) unsigned char smem_raw[];')
+    if self.flat:
+      p.println('// input queue of this warp: %d boxes of %d rows per input, '
+                'one mbarrier per box' % (lay.groups, lay.box_rows))
+      p.println('unsigned char* const queue = smem_raw + (threadIdx.x >> 5) * '
+                '%d;' % lay.warp_bytes)
+      p.println('uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw + '
+                '%d) + (threadIdx.x >> 5) * %d;' % (lay.bar_offset, lay.groups))
+      p.println('(void)queue; (void)bars;')
+    elif lay.total:
       for node in sched.nodes:
         if node.index in lay.ring_offset:
           p.println('%s* const ring_%s = reinterpret_cast<%s*>(smem_raw + %d);'
@@ -303,83 +329,121 @@ class _Emitter:
       for slot in range(self.U):
         p.println('%s h_%s_%d[%d][%d] = {};' % (
             self.ctype(node), node.ident, slot, self.VPT, self.V))
-      if node.staged:
-        for slot in range(self.U):
-          p.println('soda::Raw<%s, %d> g_%s_%d[%d] = {};   // rows in flight' %
-                    (node.c_type, self.V, node.ident, slot, self.VPT))
       if sched.paired and node.is_input:
         p.println('%s fb_%s[%d][%d] = {};   // newest output row of lane A, '
                   'input of lane B' % (node.c_type, node.ident, self.VPT,
                                        self.V))
     p.println()
 
-  # ---- 2-D input path: straight from HBM into the history --------------------
-  def emit_row_load(self, phase, rel_code, age):
-    """Fetch row ``base + rel`` of every input into the slot of ``age``; the
-    per-input pointers ``lp<k>`` walk down the rows with the calls.  Rows and
-    columns outside the grid read as 0 (a conditional load that kept the old
-    value instead would keep every dead slot alive in a register)."""
-    p, sched, V = self.p, self.sched, self.V
+  # ---- 2-D input path: per-warp TMA queue in shared memory --------------------
+  def flat_issue(self, box_code):
+    """Lane 0 requests box ``box_code`` (rows box * B .. box * B + B - 1 of
+    this chunk) of every input into its slots."""
+    p, lay = self.p, self.lay
+    G, B = lay.groups, lay.box_rows
+    p.println('uint64_t* const bar = &bars[(%s) & %d];' % (box_code, G - 1))
+    p.println('soda::mbar_expect_tx(bar, %d);' % (
+        B * sum(lay.row_bytes.values())))
+    for node in lay.loaded_inputs:
+      p.println('soda::tma_load(queue + %d + ((%s) & %d) * %d, &a.in_map[%d], '
+                'bar, org0, base + (%s) * %d);' % (
+                    lay.queue_offset[node.index], box_code, G - 1,
+                    B * lay.row_bytes[node.index], node.input_index, box_code,
+                    B))
+
+  def flat_plain_load(self, rel_code):
+    """kTma = false: row ``base + rel`` of every input, cell by cell, into the
+    ``nx_`` registers; cells outside the grid read as 0."""
+    p, lay, V = self.p, self.lay, self.V
     p.println('const bool lrow_in = static_cast<unsigned>(base + (%s)) < '
               'static_cast<unsigned>(a.dims[%d]);' % (rel_code, self.s))
-    for node in sched.inputs:
-      if node.hist_oldest is None:
-        continue
+    for node in lay.loaded_inputs:
       k = node.input_index
-      if node.staged:
-        dst = '%s[0]' % self.raw(node, phase, age)
-        p.println('if (kTma)')
-        p.do_scope()
-        # zero first, then the conditional load: the other order parks the
-        # warp on the load's scoreboard (write-after-write on its registers)
-        p.println('soda::raw_zero<%s, %d>(%s);' % (node.c_type, V, dst))
-        p.println('if (lrow_in && xin[0]) soda::ld_stream_raw<%s, %d>(%s, '
-                  'lp%d);' % (node.c_type, V, dst, k))
-        p.un_scope()
-        p.println('else')
-        p.do_scope()
-        p.println('%s t[%d];' % (node.c_type, V))
-        p.println('#pragma unroll')
-        p.println('for (int k = 0; k < %d; ++k)' % V)
-        p.println('  t[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
-                  'a.dims[0]) ? lp%d[k] : %s(0);' % (k, node.c_type))
-        p.println('soda::raw_pack<%s, %d>(%s, t);' % (node.c_type, V, dst))
-        p.un_scope()
-        p.println('lp%d += a.stride[%d];' % (k, self.s))
-        continue
-      dst = '%s[0]' % self.hist(node, phase, age)
-      p.println('if (kTma)')
-      p.do_scope()
-      p.println('soda::fill_zero<%s, %d>(%s);' % (node.c_type, V, dst))
-      p.println('if (lrow_in && xin[0]) soda::ld_stream<%s, %d>(%s, lp%d);' % (
-          node.c_type, V, dst, k))
-      p.un_scope()
-      p.println('else')
-      p.do_scope()
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)
-      p.println('  %s[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
-                'a.dims[0]) ? lp%d[k] : %s(0);' % (dst, k, node.c_type))
-      p.un_scope()
+      p.println('  nx_%s[k] = (lrow_in && gx[0] + k >= 0 && gx[0] + k < '
+                'a.dims[0]) ? lp%d[k] : %s(0);' % (node.ident, k, node.c_type))
       p.println('lp%d += a.stride[%d];' % (k, self.s))
 
   def emit_flat_prologue(self):
-    p = self.p
-    for node in self.sched.inputs:
-      if node.hist_oldest is None:
-        continue
+    p, lay = self.p, self.lay
+    G, B = lay.groups, lay.box_rows
+    for node in lay.loaded_inputs:
+      p.println('%s nx_%s[%d] = {};   // kTma = false: the next row' % (
+          node.c_type, node.ident, self.V))
       p.println('const %s* lp%d = static_cast<const %s*>(a.in_ptr[%d]) + '
-                'base * a.stride[%d] + goff[0];   // next row to fetch' % (
+                'base * a.stride[%d] + goff[0];' % (
                     node.c_type, node.input_index, node.c_type,
                     node.input_index, self.s))
-    p.println('// rows 0 .. %d of this chunk are in flight before the loop '
-              'starts' % (self.P - 1))
-    for rel in range(self.P):
-      p.do_scope()
-      # step `rel` will find this row at age 0, i.e. in slot rel mod period
-      self.emit_row_load(rel, '%d' % rel, 0)
-      p.un_scope()
+    p.println('if (kTma)')
+    p.do_scope()
+    p.println('if (lane == 0)')
+    p.do_scope()
+    for node in lay.loaded_inputs:
+      p.println('soda::tma_prefetch_desc(&a.in_map[%d]);' % node.input_index)
+    p.println('for (int n = 0; n < %d; ++n) soda::mbar_init(&bars[n], 1);' % G)
+    p.println('soda::mbar_fence_init();')
+    p.println('soda::fence_proxy_async();')
+    p.println('// the first %d boxes are in flight before the loop starts' %
+              (G - 2))
+    p.println('for (int n = 0; n < %d && n * %d < steps; ++n)' % (G - 2, B))
+    p.do_scope()
+    self.flat_issue('n')
+    p.un_scope()
+    p.un_scope()
+    p.println('__syncwarp();')
+    p.un_scope()
+    p.println('else')
+    p.do_scope()
+    self.flat_plain_load('0')
+    p.un_scope()
     p.println()
+
+  def emit_flat_input(self, phase):
+    """Start of a step: request row ii + prefetch, take row ii."""
+    p, sched, lay, V = self.p, self.sched, self.lay, self.V
+    R, G, B = lay.slots, lay.groups, lay.box_rows
+    p.println('if (kTma && (ii & %d) == 0)' % (B - 1))
+    p.do_scope()
+    p.println('// box ii / %d starts here; the box requested now replaces the '
+              'one read %d .. %d steps ago' % (B, B + 1, 2 * B))
+    p.println('const int box = ii >> %d;' % _log2(B))
+    p.println('__syncwarp();')
+    p.println('if (lane == 0 && (box + %d) * %d < steps)' % (G - 2, B))
+    p.do_scope()
+    self.flat_issue('box + %d' % (G - 2))
+    p.un_scope()
+    p.println('soda::mbar_wait(&bars[box & %d], (box >> %d) & 1);' % (
+        G - 1, _log2(G)))
+    p.un_scope()
+    for node in lay.loaded_inputs:
+      dst = '%s[0]' % self.hist(node, phase, 0)
+      p.do_scope()
+      p.println('%s t[%d];' % (node.c_type, V))
+      p.println('if (kTma)')
+      p.println('  soda::ld_pack<%s, %d>(t, reinterpret_cast<const %s*>(queue + '
+                '%d + (ii & %d) * %d) + lane * %d);' % (
+                    node.c_type, V, node.c_type, lay.queue_offset[node.index],
+                    R - 1, lay.row_bytes[node.index], V))
+      p.println('else')
+      p.do_scope()
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k) t[k] = nx_%s[k];' % (
+          V, node.ident))
+      p.un_scope()
+      p.println('#pragma unroll')
+      p.println('for (int k = 0; k < %d; ++k)' % V)
+      if sched.paired:
+        # lane A reads the input, lane B the newest output row of lane A
+        p.println('  %s[k] = soda::make_f32x2(t[k], fb_%s[0][k]);' % (
+            dst, node.ident))
+      else:
+        p.println('  %s[k] = t[k];' % dst)
+      p.un_scope()
+    p.println('if (!kTma)')
+    p.do_scope()
+    self.flat_plain_load('ii + 1')
+    p.un_scope()
 
   # ---- 3-D input path: TMA into a shared ring --------------------------------
   def tma_issue(self, rel_code):
@@ -462,27 +526,7 @@ class _Emitter:
   def emit_step(self, phase):
     p, sched, lay, V = self.p, self.sched, self.lay, self.V
     if self.flat:
-      # request the row `prefetch` steps ahead; it lands in the slot that
-      # step ii + prefetch reads as age 0
-      p.do_scope()
-      self.emit_row_load(phase, 'ii + %d' % self.P, -self.P)
-      p.un_scope()
-      # the row that arrived for this step leaves the staging ring: sub-word
-      # cells are unpacked, paired kernels join it with lane B's input row
-      for node in sched.inputs:
-        if node.hist_oldest is None or not node.staged:
-          continue
-        p.println('#pragma unroll')
-        p.println('for (int k = 0; k < %d; ++k)' % V)
-        if sched.paired:
-          p.println('  %s[0][k] = soda::make_f32x2(soda::raw_get<%s, %d>('
-                    '%s[0], k), fb_%s[0][k]);' % (
-                        self.hist(node, phase, 0), node.c_type, V,
-                        self.raw(node, phase, 0), node.ident))
-        else:
-          p.println('  %s[0][k] = soda::raw_get<%s, %d>(%s[0], k);' % (
-              self.hist(node, phase, 0), node.c_type, V,
-              self.raw(node, phase, 0)))
+      self.emit_flat_input(phase)
     elif lay.loaded_inputs:
       p.println('if (kTma)')
       p.do_scope()

@@ -440,6 +440,7 @@ class Schedule:
 # --- the register-streaming schedule -----------------------------------------
 
 _PAIR_TOKEN = None
+FLAT_GROUPS = 4   # boxes in the input queue of a 2-D register kernel
 
 
 def pairing_obstacle(program, depth):
@@ -490,9 +491,12 @@ class RegSchedule(Schedule):
     history** of the parent (the last few streamed planes of its own cells);
     ``dx != 0`` takes the missing cells from the neighbouring lanes with warp
     shuffles — this is the whole story for 2-D programs, which use no shared
-    memory and no block barrier at all: a block is ``warps`` independent
-    strips, inputs come straight from HBM with 128-bit loads issued
-    ``prefetch`` rows ahead into the history registers;
+    memory for anything but the input queue and no block barrier at all: a
+    block is ``warps`` independent strips; each warp keeps a private
+    shared-memory ring of ``flat_slots`` input rows that one elected lane
+    fills by TMA, a box of ``flat_box`` rows per request, ``prefetch`` rows
+    ahead (one mbarrier per box), so rows in flight cost no registers and the HBM latency is covered however deep the
+    fused chain is;
   * only a load with an in-plane offset in a dimension other than 0 (3-D:
     dy != 0) goes through a **shared-memory plane ring** of the parent, which
     the producing stage writes next to its registers; such a parent must have
@@ -509,11 +513,25 @@ class RegSchedule(Schedule):
   style = 'reg'
 
   def __init__(self, program, depth, vec, warps, tile_rest=(), prefetch=2,
-               paired=False, min_blocks=1):
+               paired=False, min_blocks=1, groups=None):
     self.warps = warps
     self.min_blocks = min_blocks     # resident blocks per SM to compile for
     self.tiles_per_block = warps if program.dim == 2 else 1
     self.input_in_smem = program.dim > 2
+    # 2-D: the per-warp input queue holds FLAT_GROUPS boxes of `flat_box`
+    # rows; one TMA request brings a whole box (requests of a single 512-byte
+    # row are bound by the TMA unit's request rate, ~1 per 50 cycles per SM).
+    # A box is requested `prefetch` = (FLAT_GROUPS - 2) boxes ahead of its
+    # first use, into the slots of the box consumed before the previous one.
+    self.flat_groups = groups or FLAT_GROUPS
+    if self.flat_groups < 3 or self.flat_groups & (self.flat_groups - 1):
+      raise util.SemanticError('the input queue holds 4, 8, 16.. boxes')
+    self.flat_box = max(1, prefetch // (self.flat_groups - 2)) \
+        if program.dim == 2 else 0
+    self.flat_slots = self.flat_groups * self.flat_box
+    if self.flat_box & (self.flat_box - 1):
+      raise util.SemanticError('prefetch must be %d x a power of two' %
+                               (self.flat_groups - 2))
     self.paired = paired
     if paired:
       why = pairing_obstacle(program, depth)
@@ -555,17 +573,6 @@ class RegSchedule(Schedule):
       # registers hold the rows of age node.delay .. hist_oldest
       node.hist_oldest = max(reg_ages) if reg_ages else None
       node.hist_newest = node.delay
-      node.staged = False
-      if node.is_input and not self.input_in_smem and reg_ages:
-        if self.paired or node.elem_size < 4:
-          # rows in flight wait in a staging ring as loaded (ages -prefetch
-          # .. 0) and are unpacked — sub-word cells to one register each,
-          # paired kernels: joined with lane B's row — when they turn age 0;
-          # converting on arrival would stall on the load just issued
-          node.staged = True
-          spans.append(self.prefetch + 1)
-        else:
-          node.hist_newest = -self.prefetch    # rows in flight from HBM
       if node.is_input and self.input_in_smem:
         node.ring_depth = (_pow2(max(smem_ages + [0]) + self.prefetch + 1)
                            if node.consumers else 0)

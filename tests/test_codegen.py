@@ -29,8 +29,8 @@ def test_kernel_and_host_to_files_and_stdout(tmp_path):
          'const char* xclbin)' in done.stdout
   text = kernel.read_text()
   assert '__global__ void __launch_bounds__' in text
-  # 2-D programs stream through registers: 128-bit loads, warp shuffles
-  assert 'soda::ld_stream_raw<uint16_t, 8>(' in text and 'soda::shfl_down<' in text
+  # 2-D programs stream through registers: TMA input queue, warp shuffles
+  assert 'soda::tma_load(queue' in text and 'soda::shfl_down<' in text
   # the reference-lowered expressions, operands mapped to register histories
   assert '/ 3)' in text and 'r[0] = (' in text
   ring = tmp_path / 'ring.cu'
