@@ -60,46 +60,73 @@ def load_stencil(iterate=None):
 
 
 class ClockSampler:
-  """nvidia-smi clocks and throttle reasons while the timed region runs."""
-  QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-           'clocks_event_reasons.hw_thermal_slowdown,'
-           'clocks_event_reasons.sw_thermal_slowdown,'
-           'clocks_event_reasons.sw_power_cap')
+  """SM clock and throttle reasons sampled WHILE the timed region runs: NVML
+  polled every 2 ms from a thread (nvidia-smi's fastest loop is slower than
+  the whole timed region); `nvidia-smi` once as a fallback."""
+  REASONS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40),
+             ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
   def __init__(self, index):
-    self.rows = []
-    self._proc = None
+    self.index = index
+    self.clocks, self.masks, self.max_mhz = [], 0, None
+    self._stop = threading.Event()
+    self._thread = None
     try:
-      self._proc = subprocess.Popen(
-          ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
-           '--format=csv,noheader,nounits', '-lms', '100'],
-          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-      self._thread = threading.Thread(target=self._read, daemon=True)
+      import pynvml
+      pynvml.nvmlInit()
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      if visible:
+        index = int(visible.split(',')[index])
+      self._nvml = pynvml
+      self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(
+          self._handle, pynvml.NVML_CLOCK_SM)
+      self._thread = threading.Thread(target=self._poll, daemon=True)
       self._thread.start()
-    except OSError:
-      self._proc = None
+    except Exception:   # pylint: disable=broad-except
+      self._nvml = None
 
-  def _read(self):
-    for line in self._proc.stdout:
-      self.rows.append([c.strip() for c in line.split(',')])
+  def _poll(self):
+    nv = self._nvml
+    while not self._stop.is_set():
+      try:
+        self.clocks.append(nv.nvmlDeviceGetClockInfo(self._handle,
+                                                     nv.NVML_CLOCK_SM))
+        self.masks |= nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+      except Exception:   # pylint: disable=broad-except
+        break
+      time.sleep(0.002)
+
+  def _smi_once(self):
+    query = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+    try:
+      out = subprocess.run(
+          ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + query,
+           '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
+          stderr=subprocess.DEVNULL, text=True, timeout=20).stdout
+      row = [c.strip() for c in out.strip().split(',')]
+      return {'sm_mhz': int(row[0]), 'sm_max_mhz': int(row[1]),
+              'reasons': [n for (n, _), c in zip(self.REASONS, row[2:6])
+                          if c.lower().startswith('active')],
+              'samples': 1, 'source': 'nvidia-smi after the timed region'}
+    except Exception:   # pylint: disable=broad-except
+      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable'],
+              'samples': 0}
 
   def stop(self):
-    if self._proc is None:
-      return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['unavailable']}
-    self._proc.terminate()
-    self._thread.join(timeout=2)
-    clocks = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-    reasons = set()
-    names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-             'sw_power_cap')
-    for row in self.rows:
-      for name, cell in zip(names, row[2:6]):
-        if cell.lower().startswith('active'):
-          reasons.add(name)
-    top = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-    return {'sm_mhz': clocks[len(clocks) // 2] if clocks else None,
-            'sm_max_mhz': max(top) if top else None,
-            'reasons': sorted(reasons), 'samples': len(clocks)}
+    self._stop.set()
+    if self._thread is not None:
+      self._thread.join(timeout=2)
+    if not self.clocks:
+      return self._smi_once()
+    clocks = sorted(self.clocks)
+    return {'sm_mhz': clocks[len(clocks) // 2], 'sm_max_mhz': self.max_mhz,
+            'reasons': [n for n, bit in self.REASONS if self.masks & bit],
+            'samples': len(clocks), 'source': 'NVML polled during the timed '
+            'region'}
 
 
 def cpu_port_gcells(iterate, threads=None):
@@ -219,11 +246,13 @@ def main():
     runner.load_local([dev_in])
     step = lambda: runner.run(iterate)
     launches_per_step = runner.launches_per_run(iterate)
+    passes_per_step = len(runner.plan(iterate))
+    depth_planned = runner.plan(iterate)[0]
   else:
     dev_out = torch.empty(shape, dtype=torch.float32, device='cuda')
     step = lambda: library.run_device([dev_in], [dev_out], dims, iterate,
                                       stream)
-    launches_per_step = None
+    launches_per_step = passes_per_step = depth_planned = None
 
   # ---- device-resident timing ------------------------------------------------
   for _ in range(args.warmup):
@@ -242,8 +271,10 @@ def main():
   value = cells * world * iterate / (ms_per_step * 1e6)     # GCell/s
   stats = library.stats
   if launches_per_step is None:
-    launches_per_step = stats['launches']
-  depth = stats['depth']
+    launches_per_step = passes_per_step = stats['launches']
+  # slab runs launch faces and interior separately: a "pass" is one sweep of
+  # the whole slab by the depth-T kernel, however many launches it took
+  depth = depth_planned or stats['depth']
 
   # ---- end to end through the C ABI with host buffers ------------------------
   host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True)
@@ -270,7 +301,7 @@ def main():
     return
 
   peak, peak_kind = measured_hbm_gbs()
-  launch_ms = ms_per_step / launches_per_step
+  launch_ms = ms_per_step / passes_per_step
   achieved = cells * BYTES_PER_CELL / (launch_ms * 1e6)        # GB/s
   traffic = None
   try:
@@ -287,6 +318,7 @@ def main():
       'data': 'synthetic (reference initialiser pattern, host.py:1033-1051)',
       'config': dict(workload_config(world), temporal_depth=depth,
                      launches_per_step=launches_per_step,
+                     passes_per_step=passes_per_step,
                      threads=stats['threads'], smem_bytes=stats['smem_bytes'],
                      tma=bool(stats['used_tma'])),
       'e2e': {'value': e2e_value, 'unit': 'GCell/s', 'ms_per_step': e2e_ms,

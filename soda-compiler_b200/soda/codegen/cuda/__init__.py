@@ -33,6 +33,7 @@ SUPPORTED_TYPES = {
     'float', 'float32', 'double', 'float64'}
 SMEM_LIMIT = 227 * 1024
 REG_HISTORY_BUDGET = 80   # registers per thread held across steps (2-D)
+REG_HISTORY_3D = 64       # 3-D: above this, one vector per thread
 
 
 def add_arguments(parser):
@@ -178,11 +179,17 @@ def _make_reg_schedule(program, depth, options, limit):
   for rest in rests:
     rows = math.prod(rest)
     for prefetch in prefetches:
-      warps = (options.threads // 32 if options.threads
-               else max(1, min(16, rows // 2)))
+      # two vectors per thread halve the shuffles and barriers per cell, but
+      # only while the register histories leave room for the working set
+      warp_choices = ([options.threads // 32] if options.threads else
+                      [max(1, min(16, rows // 2)), max(1, min(16, rows))])
       try:
-        sched = plan_mod.RegSchedule(program, depth, vec, warps, rest,
-                                     prefetch)
+        for warps in warp_choices:
+          sched = plan_mod.RegSchedule(program, depth, vec, warps, rest,
+                                       prefetch,
+                                       min_blocks=options.min_blocks or 1)
+          if history_registers(sched) <= REG_HISTORY_3D:
+            break
         total = kernel_reg_mod.Layout(sched).total
       except util.SemanticError as e:
         problem = problem or e

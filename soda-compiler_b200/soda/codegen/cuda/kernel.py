@@ -359,7 +359,7 @@ def _emit_stage(p, sched, lay, node):
   p.do_scope()
   for let in lets:
     p.println(let)
-  p.println('r[k] = %s;' % expr)
+  p.println('r[k] = soda::store_cast<%s>(%s);' % (node.c_type, expr))
   p.un_scope()
   if node.index in lay.ring_offset:
     p.println('soda::st_pack<%s, %d>(ring_%s + ((i + (%d)) & %d) * %d + pos[j],'

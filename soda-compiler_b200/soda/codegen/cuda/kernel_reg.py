@@ -654,7 +654,11 @@ class _Emitter:
         p.do_scope()
         for let in lets:
           p.println(let)
-      p.println('%s[%d] = %s;' % (target, k, expr))
+      if sched.paired:
+        p.println('%s[%d] = %s;' % (target, k, expr))
+      else:
+        p.println('%s[%d] = soda::store_cast<%s>(%s);' % (
+            target, k, node.c_type, expr))
       if lets:
         p.un_scope()
     if node.index in lay.ring_offset:

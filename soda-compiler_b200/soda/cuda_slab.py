@@ -131,6 +131,11 @@ class SlabRunner:
         ops.append(dist.P2POp(dist.irecv, tensor[b:b + self.ghost_hi],
                               self.rank + 1, self.group))
     ops = [op for op in ops if op.tensor.numel() > 0]
+    for op in ops:
+      # NCCL has no unsigned 16/32/64-bit types: planes travel as bytes
+      # (slices of whole planes are contiguous, so the view is free)
+      if op.tensor.dtype in (torch.uint16, torch.uint32, torch.uint64):
+        op.tensor = op.tensor.view(torch.uint8)
     return dist.batch_isend_irecv(ops) if ops else []
 
   # ---- compute ----------------------------------------------------------

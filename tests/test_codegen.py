@@ -32,14 +32,14 @@ def test_kernel_and_host_to_files_and_stdout(tmp_path):
   # 2-D programs stream through registers: TMA input queue, warp shuffles
   assert 'soda::tma_load(queue' in text and 'soda::shfl_down<' in text
   # the reference-lowered expressions, operands mapped to register histories
-  assert '/ 3)' in text and 'r[0] = (' in text
+  assert '/ 3)' in text and 'r[0] = soda::store_cast<uint16_t>((' in text
   ring = tmp_path / 'ring.cu'
   done = sodac(common.bench_path('blur'), '--cuda-kernel', str(ring),
                '--cuda-style', 'ring')
   assert done.returncode == 0, done.stderr
   text = ring.read_text()
   assert 'soda::tma_load(' in text and 'soda::mbar_wait(' in text
-  assert text.count('r[k] = (') == 2
+  assert text.count('r[k] = soda::store_cast<uint16_t>((') == 2
   assert 'int blur(' in host.read_text()
   assert 'soda_cuda_run' in host.read_text()
 

@@ -39,6 +39,10 @@ CASES = [
     ('heat3d', 3, (192, 48, 33), {'depth': 2}),      # 2 + 1 remainder
     ('heat3d', 1, (256, 128, 64), {}),
     ('denoise3d', 1, (128, 48, 24), {}),
+    # millions of `1.0f / sqrt(x)` cells: the float-arithmetic rounding decision
+    # (soda::RecipSqrtF32) and its FP64 fallback both occur
+    ('denoise2d', 1, (4096, 1536), {}),
+    ('denoise3d', 1, (256, 192, 96), {}),
 ]
 
 

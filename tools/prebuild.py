@@ -40,14 +40,16 @@ def main():
   else:
     import test_parity_gpu
     import test_slab_gpu
+    import test_rsqrt_exact
+    print('%-40s %s' % ('rsqrt check', os.path.relpath(
+        test_rsqrt_exact.build_check(), ROOT)))
     import __graft_entry__ as entry
     for name, iterate, _, options in test_parity_gpu.CASES:
       jobs.append((name, iterate, options))
     for name, iterate, _ in test_parity_gpu.REF_CASES:
       jobs.append((name, iterate, {}))
-    del test_slab_gpu
-    jobs += [('jacobi2d', 16, {'depth': 4}), ('jacobi2d', 7, {'depth': 4}),
-             ('heat3d', 4, {'depth': 2}), ('denoise2d', 1, {})]
+    for name, iterate, options, _ in test_slab_gpu.CASES:
+      jobs.append((name, iterate, options))
     jobs += [(n, None, {}) for n in entry.BENCHMARKS]
     jobs += [(n, it, {}) for n, it in entry.EXTRA_BUILDS]
   unique = []
