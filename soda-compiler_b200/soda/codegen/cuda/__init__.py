@@ -34,6 +34,7 @@ SUPPORTED_TYPES = {
 SMEM_LIMIT = 227 * 1024
 REG_HISTORY_BUDGET = 80   # registers per thread held across steps (2-D)
 REG_HISTORY_3D = 64       # 3-D: above this, one vector per thread
+FLAT_SMEM_TARGET = 75 * 1024   # 2-D input queues per block: 3 blocks per SM
 
 
 def add_arguments(parser):
@@ -158,10 +159,19 @@ def _make_reg_schedule(program, depth, options, limit):
     paired = (options.paired if options.paired is not None else
               plan_mod.pairing_obstacle(program, depth) is None)
     groups = options.groups or plan_mod.FLAT_GROUPS
+    # rows per TMA box (measured, profiles/r1i): 6 keeps six blocks resident;
+    # paired kernels hold fewer, fatter warps and want deeper queues
     prefetch = options.prefetch if options.prefetch is not None else (
-        4 * (groups - 2))
-    sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
-                                 paired=paired, groups=groups)
+        (9 if paired else 6) * (groups - 2))
+    while True:
+      sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
+                                   paired=paired, groups=groups)
+      # keep three blocks per SM resident: shorter boxes if the queues of all
+      # inputs do not fit (programs with several inputs or long periods)
+      if (options.prefetch is not None or sched.flat_box <= sched.period or
+          kernel_reg_mod.Layout(sched).total <= FLAT_SMEM_TARGET):
+        break
+      prefetch = (sched.flat_box - sched.period) * (groups - 2)
     sched.min_blocks = options.min_blocks or default_min_blocks(sched)
     return sched
   if options.tile:

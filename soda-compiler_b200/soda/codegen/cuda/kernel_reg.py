@@ -31,6 +31,7 @@ compile-time register names: the row computed k steps ago sits in slot
 ``(phase - k) mod period``.
 """
 import collections
+import re
 
 from haoda import util
 from soda.codegen.cuda import plan as plan_mod
@@ -120,11 +121,51 @@ def _render(stage, ref_code, k):
   return lets, stage.expr.visit(swap).c_expr
 
 
+_INT_TYPES = {'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32',
+              'int64'}
+# + - * on tensor cells and plain integer literals: the low w bits of such an
+# expression depend only on the low w bits of its operands
+_RING_TOKEN = re.compile(r'\s+|[-+*()]|@|(?:0[xX][0-9a-fA-F]+|\d+)[uU]?(?![.\w])')
+
+
+def ring_expression(stage, program):
+  """Is the stage's lowered C expression a polynomial (+ - *) in integer
+  tensor cells and integer literals?  Judged on the emitted text, which is
+  what the reference evaluates (its parenthesisation is not the tree's)."""
+  if stage.lets or program.types[stage.name] not in _INT_TYPES:
+    return False
+  for load in stage.loads:
+    if program.types.get(load.parent) not in _INT_TYPES:
+      return False
+  _, text = stage.render(lambda load: '@')
+  pos = 0
+  while pos < len(text):
+    match = _RING_TOKEN.match(text, pos)
+    if not match:
+      return False
+    pos = match.end()
+  return True
+
+
 class _Emitter:
 
   def __init__(self, p, sched):
     self.p = p
     self.sched = sched
+    # Lazy truncation.  An 8- or 16-bit integer tensor is kept in 32-bit
+    # registers whose upper bits are unspecified ("loose"): an input cell is
+    # the loaded word shifted down, a stage result is not narrowed.  A stage
+    # that is a polynomial in its operands and no wider than them reads loose
+    # values as they are (arithmetic modulo 2^32 agrees with the reference's
+    # int arithmetic on the bits that are kept); any other stage reads them
+    # through a cast to the declared type.  Stores narrow once, when packing.
+    program = sched.program
+    self.loose = {
+        node.index: (not sched.paired and node.elem_size < 4 and
+                     program.types[node.name] in _INT_TYPES)
+        for node in sched.nodes}
+    self.ring = {node.index: ring_expression(node.stage, program)
+                 for node in sched.stage_nodes}
     self.lay = Layout(sched)
     self.s = sched.sdim
     self.V = sched.vec
@@ -144,6 +185,8 @@ class _Emitter:
   def ctype(self, node):
     """Type of a cell of ``node`` in registers: a pair of float32 (iteration
     k, iteration k + depth/2) when the schedule pairs iterations."""
+    if self.loose[node.index]:
+      return 'uint32_t'
     return 'soda::f32x2' if self.sched.paired else node.c_type
 
   def ring_slot(self, node, age):
@@ -191,12 +234,18 @@ class _Emitter:
     else:
       self.emit_tma_prologue()
     self.emit_output_windows()
-    p.println('for (int i = 0; i < steps; i += %d)' % self.U)
+    # `steps` is a whole number of trips: the surplus steps compute rows no
+    # block stores (beyond mine_hi) from rows that read as 0 or as real data
+    trip = lay.box_rows if self.flat else self.U
+    if self.flat:
+      p.println('for (int i = 0, box = 0; i < steps; i += %d, ++box)' % trip)
+    else:
+      p.println('for (int i = 0; i < steps; i += %d)' % trip)
     p.do_scope()
-    for phase in range(self.U):
-      if phase:
-        p.println('if (i + %d >= steps) break;' % phase)
-      p.println('// ---- phase %d of %d' % (phase, self.U))
+    if self.flat:
+      self.emit_flat_box()
+    for phase in range(trip):
+      p.println('// ---- step %d of %d' % (phase, trip))
       p.do_scope()
       p.println('const int ii = i + %d;' % phase)
       self.emit_step(phase)
@@ -230,8 +279,11 @@ class _Emitter:
     p.println('const int r1 = min(a.row_end, r0 + a.chunk_rows);')
     p.println('const int base = r0 - %d;   // streamed coordinate of step 0' %
               sched.lead)
-    p.println('const int steps = (r1 - r0) + %d;' %
-              (sched.lead + sched.out_delay))
+    trip = sched.flat_box if self.flat else self.U
+    p.println('// steps to run: (r1 - r0) + %d, rounded up to whole trips of '
+              'the streamed loop' % (sched.lead + sched.out_delay))
+    p.println('const int steps = ((r1 - r0) + %d) / %d * %d;' % (
+        sched.lead + sched.out_delay + trip - 1, trip, trip))
     p.println()
     p.println('// per-thread vectors: position in the plane, offset in HBM, '
               'cells this tile')
@@ -399,15 +451,14 @@ class _Emitter:
     p.un_scope()
     p.println()
 
-  def emit_flat_input(self, phase):
-    """Start of a step: request row ii + prefetch, take row ii."""
-    p, sched, lay, V = self.p, self.sched, self.lay, self.V
-    R, G, B = lay.slots, lay.groups, lay.box_rows
-    p.println('if (kTma && (ii & %d) == 0)' % (B - 1))
+  def emit_flat_box(self):
+    """Start of a trip: request the box G - 2 ahead, wait for this one."""
+    p, lay = self.p, self.lay
+    G, B = lay.groups, lay.box_rows
+    p.println('if (kTma)')
     p.do_scope()
-    p.println('// box ii / %d starts here; the box requested now replaces the '
-              'one read %d .. %d steps ago' % (B, B + 1, 2 * B))
-    p.println('const int box = ii >> %d;' % _log2(B))
+    p.println('// rows i .. i + %d are box `box`; the box requested now '
+              'replaces the one read %d .. %d steps ago' % (B - 1, B + 1, 2 * B))
     p.println('__syncwarp();')
     p.println('if (lane == 0 && (box + %d) * %d < steps)' % (G - 2, B))
     p.do_scope()
@@ -417,14 +468,40 @@ class _Emitter:
         G - 1, _log2(G)))
     p.un_scope()
     for node in lay.loaded_inputs:
+      p.println('const unsigned char* const rows_%s = queue + %d + (box & %d) * '
+                '%d + lane * %d;' % (
+                    node.ident, lay.queue_offset[node.index], G - 1,
+                    B * lay.row_bytes[node.index], self.V * node.elem_size))
+
+  def emit_flat_input(self, phase):
+    """Start of a step: take row ii (row `phase` of the current box)."""
+    p, sched, lay, V = self.p, self.sched, self.lay, self.V
+    for node in lay.loaded_inputs:
       dst = '%s[0]' % self.hist(node, phase, 0)
       p.do_scope()
-      p.println('%s t[%d];' % (node.c_type, V))
-      p.println('if (kTma)')
-      p.println('  soda::ld_pack<%s, %d>(t, reinterpret_cast<const %s*>(queue + '
-                '%d + (ii & %d) * %d) + lane * %d);' % (
-                    node.c_type, V, node.c_type, lay.queue_offset[node.index],
-                    R - 1, lay.row_bytes[node.index], V))
+      loose = self.loose[node.index] and V * node.elem_size % 4 == 0
+      if loose:
+        # whole words; a cell is its word shifted down, upper bits loose
+        per = 4 // node.elem_size
+        p.println('uint32_t t[%d];' % V)
+        p.println('if (kTma)')
+        p.do_scope()
+        p.println('uint32_t words[%d];' % (V // per))
+        p.println('soda::ld_pack<uint32_t, %d>(words, reinterpret_cast<const '
+                  'uint32_t*>(rows_%s + %d));' % (
+                      V // per, node.ident,
+                      phase * lay.row_bytes[node.index]))
+        p.println('#pragma unroll')
+        p.println('for (int k = 0; k < %d; ++k) t[k] = words[k / %d] >> '
+                  '(%d * (k %% %d));' % (V, per, 8 * node.elem_size, per))
+        p.un_scope()
+      else:
+        p.println('%s t[%d];' % (node.c_type, V))
+        p.println('if (kTma)')
+        p.println('  soda::ld_pack<%s, %d>(t, reinterpret_cast<const %s*>('
+                  'rows_%s + %d));' % (
+                      node.c_type, V, node.c_type, node.ident,
+                      phase * lay.row_bytes[node.index]))
       p.println('else')
       p.do_scope()
       p.println('#pragma unroll')
@@ -542,9 +619,20 @@ class _Emitter:
           continue
         p.println('#pragma unroll')
         p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
-        p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %s * %d + pos[j]);'
-                  % (node.c_type, V, self.hist(node, phase, 0), node.ident,
-                     self.ring_slot(node, 0), self.PLANE))
+        if self.loose[node.index]:
+          p.do_scope()
+          p.println('%s t[%d];' % (node.c_type, V))
+          p.println('soda::ld_pack<%s, %d>(t, ring_%s + %s * %d + pos[j]);' % (
+              node.c_type, V, node.ident, self.ring_slot(node, 0), self.PLANE))
+          p.println('#pragma unroll')
+          p.println('for (int k = 0; k < %d; ++k) %s[j][k] = t[k];' % (
+              V, self.hist(node, phase, 0)))
+          p.un_scope()
+        else:
+          p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %s * %d + '
+                    'pos[j]);' % (node.c_type, V, self.hist(node, phase, 0),
+                                  node.ident, self.ring_slot(node, 0),
+                                  self.PLANE))
     self.shuffled = {}     # (node index, age, element) -> variable, this step
     for node in sched.stage_nodes:
       self.emit_stage(node, phase)
@@ -640,9 +728,13 @@ class _Emitter:
         return 'w%d[%d]' % (g, k + off[0] - xlo)
       age = node.delay - off[s]
       c = k + off[0]
-      if 0 <= c < V:
-        return '%s[j][%d]' % (self.hist(parent, phase, age), c)
-      return '%s[j]' % self.shuffled[(parent.index, age, c)]
+      code = ('%s[j][%d]' % (self.hist(parent, phase, age), c)
+              if 0 <= c < V else
+              '%s[j]' % self.shuffled[(parent.index, age, c)])
+      if self.loose[parent.index] and not (
+          self.ring[node.index] and node.elem_size <= parent.elem_size):
+        code = 'static_cast<%s>(%s)' % (parent.c_type, code)
+      return code
 
     keeps = node.hist_oldest is not None
     target = ('%s[j]' % self.hist(node, phase, node.delay)) if keeps else 'r'
@@ -656,15 +748,24 @@ class _Emitter:
           p.println(let)
       if sched.paired:
         p.println('%s[%d] = %s;' % (target, k, expr))
+      elif self.loose[node.index] and self.ring[node.index]:
+        p.println('%s[%d] = static_cast<uint32_t>(%s);' % (target, k, expr))
       else:
         p.println('%s[%d] = soda::store_cast<%s>(%s);' % (
             target, k, node.c_type, expr))
       if lets:
         p.un_scope()
     if node.index in lay.ring_offset:
+      plane = target
+      if self.loose[node.index]:
+        plane = 'narrow'
+        p.println('%s narrow[%d];' % (node.c_type, V))
+        p.println('#pragma unroll')
+        p.println('for (int k = 0; k < %d; ++k) narrow[k] = static_cast<%s>('
+                  '%s[k]);' % (V, node.c_type, target))
       p.println('soda::st_pack<%s, %d>(ring_%s + %s * %d + pos[j], %s);' % (
           node.c_type, V, node.ident, self.ring_slot(node, node.delay),
-          self.PLANE, target))
+          self.PLANE, plane))
     if node.output_index is not None and sched.paired:
       # lane A's result (iteration depth/2 - 1) feeds lane B one step later
       feeds = sched.inputs[node.output_index]
@@ -678,8 +779,8 @@ class _Emitter:
       p.do_scope()
       p.println('%s o[%d];' % (node.c_type, V))
       p.println('#pragma unroll')
-      p.println('for (int k = 0; k < %d; ++k) o[k] = %s[k]%s;' % (
-          V, target, half))
+      p.println('for (int k = 0; k < %d; ++k) o[k] = static_cast<%s>(%s[k]%s);'
+                % (V, node.c_type, target, half))
       p.println('soda::st_pack_global<%s, %d>(op%d[j], o);' % (
           node.c_type, V, n))
       p.un_scope()
@@ -691,8 +792,8 @@ class _Emitter:
       p.println('%s o[%d];' % (node.c_type, V))
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)
-      p.println('  o[k] = ((keep >> k) & 1u) ? %s[k]%s : %s(0);' % (
-          target, half, node.c_type))
+      p.println('  o[k] = ((keep >> k) & 1u) ? static_cast<%s>(%s[k]%s) : '
+                '%s(0);' % (node.c_type, target, half, node.c_type))
       p.println('if (own[j] == %du && a.vec_store)' % ((1 << V) - 1))
       p.do_scope()
       p.println('soda::st_pack_global<%s, %d>(op%d[j], o);' % (

@@ -391,8 +391,13 @@ class Schedule:
     self.window = (lo, hi)
     self.halo_lo = [max(0, -l) for l in lo]
     self.halo_hi = [max(0, h) for h in hi]
-    # dim 0 halos round up to whole vectors so owned cells stay vector aligned
+    # dim 0 halos round up to whole vectors so owned cells stay vector aligned,
+    # and to 16 bytes of every input: a TMA box that starts at a global
+    # address not aligned to 16 bytes traps (observed on B200 with 8-byte
+    # aligned tile origins: "illegal instruction" at the cp.async.bulk.tensor)
     v = self.vec
+    for node in self.inputs:
+      v = max(v, 16 // node.elem_size)
     self.tile_halo_lo = [(-(-self.halo_lo[0] // v)) * v] + self.halo_lo[1:-1]
     self.tile_halo_hi = [(-(-self.halo_hi[0] // v)) * v] + self.halo_hi[1:-1]
     self.own = [t - a - b for t, a, b in
@@ -521,17 +526,12 @@ class RegSchedule(Schedule):
     # 2-D: the per-warp input queue holds FLAT_GROUPS boxes of `flat_box`
     # rows; one TMA request brings a whole box (requests of a single 512-byte
     # row are bound by the TMA unit's request rate, ~1 per 50 cycles per SM).
-    # A box is requested `prefetch` = (FLAT_GROUPS - 2) boxes ahead of its
-    # first use, into the slots of the box consumed before the previous one.
+    # A box is requested (FLAT_GROUPS - 2) boxes (about `prefetch` rows) ahead
+    # of its first use, into the slots of the box consumed before the previous
+    # one.
     self.flat_groups = groups or FLAT_GROUPS
     if self.flat_groups < 3 or self.flat_groups & (self.flat_groups - 1):
       raise util.SemanticError('the input queue holds 4, 8, 16.. boxes')
-    self.flat_box = max(1, prefetch // (self.flat_groups - 2)) \
-        if program.dim == 2 else 0
-    self.flat_slots = self.flat_groups * self.flat_box
-    if self.flat_box & (self.flat_box - 1):
-      raise util.SemanticError('prefetch must be %d x a power of two' %
-                               (self.flat_groups - 2))
     self.paired = paired
     if paired:
       why = pairing_obstacle(program, depth)
@@ -539,6 +539,15 @@ class RegSchedule(Schedule):
         raise util.SemanticError('cannot pair iterations: ' + why)
     super().__init__(program, depth, (32 * vec,) + tuple(tile_rest), vec,
                      32 * warps, prefetch)
+    # A box is a whole number of history periods, so that one trip of the
+    # streamed loop consumes exactly one box: which row of the box a step
+    # reads and which register slot it fills are both compile-time constants.
+    self.flat_box = 0
+    if program.dim == 2:
+      want = max(1, prefetch // (self.flat_groups - 2))
+      self.flat_box = self.period * max(1, (want + self.period // 2) //
+                                        self.period)
+    self.flat_slots = self.flat_groups * self.flat_box
 
   def via_smem(self, off):
     """Does a load at offset ``off`` need the parent's shared plane?"""

@@ -43,6 +43,19 @@ CASES = [
     # (soda::RecipSqrtF32) and its FP64 fallback both occur
     ('denoise2d', 1, (4096, 1536), {}),
     ('denoise3d', 1, (256, 192, 96), {}),
+    # every tuning knob of the backend (sodac --cuda-*): narrower vectors
+    # (TMA boxes of 256 bytes), other block sizes, queue geometries, the
+    # shared-memory ring family
+    ('jacobi2d', 4, (1024, 128), {'vec': 2}),
+    ('blur', 1, (2048, 128), {'vec': 4}),
+    ('denoise2d', 1, (1024, 128), {'vec': 2}),
+    ('sobel2d', 1, (2048, 200), {'threads': 64, 'groups': 8}),
+    ('sobel2d', 1, (2048, 200), {'threads': 256, 'prefetch': 2}),
+    ('jacobi2d', 8, (2048, 260), {'depth': 8, 'prefetch': 12, 'paired': 0}),
+    ('jacobi2d', 6, (2048, 260), {'depth': 6, 'prefetch': 24}),
+    ('blur', 1, (2048, 128), {'style': 'ring'}),
+    ('heat3d', 2, (192, 48, 33), {'style': 'ring'}),
+    ('heat3d', 2, (256, 64, 40), {'tile': [128, 16], 'threads': 256}),
 ]
 
 

@@ -50,6 +50,11 @@ def main():
       jobs.append((name, iterate, {}))
     for name, iterate, options, _ in test_slab_gpu.CASES:
       jobs.append((name, iterate, options))
+    import test_types_gpu
+    for name, _, options in test_types_gpu.CASES:
+      print('%-40s %s' % ((name, options), os.path.relpath(soda_cuda.build(
+          test_types_gpu.stencil_of(name),
+          options=codegen.Options(**options)), ROOT)))
     jobs += [(n, None, {}) for n in entry.BENCHMARKS]
     jobs += [(n, it, {}) for n, it in entry.EXTRA_BUILDS]
   unique = []
