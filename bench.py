@@ -40,7 +40,7 @@ sys.path[:0] = [os.path.join(ROOT, 'soda-compiler_b200')]
 
 WORKLOAD = dict(program='jacobi2d', iterate=64, dims=(16384, 16384))
 BYTES_PER_CELL = 8          # float32 in + float32 out
-CPU_SAMPLE_ITERATE = 4      # iterations of the same grid timed on the CPU
+CPU_SAMPLE_ITERATE = 64     # iterations timed on the CPU: the whole workload
 HBM_FALLBACK_GBS = 6650.0   # B200_PROFILING.md, if MEASURED_PEAKS.json absent
 
 
