@@ -157,7 +157,7 @@ void valid_region(const ProgramDesc& prog, int iterate, const int32_t* dims,
 
 // Blocks along the streamed dimension: minimise (waves x steps per block).
 int pick_chunks(long long tile_blocks, long long resident, int rows,
-                int overhead) {
+                int overhead, int trip) {
   const int max_chunks = std::max(1, std::min(rows, 65535));
   long long best_cost = -1;
   int best = 1;
@@ -166,6 +166,10 @@ int pick_chunks(long long tile_blocks, long long resident, int rows,
     const int real_chunks = (rows + chunk_rows - 1) / chunk_rows;
     if (real_chunks != chunks) continue;
     const long long waves = (tile_blocks * chunks + resident - 1) / resident;
+    // (a block runs whole trips of its streamed loop, up to trip - 1 surplus
+    // steps; counting them here picks coarser chunks, which measured 2-7 %
+    // slower on blur, sobel2d and denoise2d: the finer grid balances the tail)
+    (void)trip;
     const long long cost = waves * (chunk_rows + overhead);
     if (best_cost < 0 || cost < best_cost) {
       best_cost = cost;
@@ -303,7 +307,8 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
   // 2-D register kernels pack `tiles_per_block` independent strips in a block
   const int per_block = std::max(1, kv->tiles_per_block);
   const long long grid_x = (tile_blocks + per_block - 1) / per_block;
-  int chunks = pick_chunks(grid_x, resident, rows, kv->lead + kv->out_delay);
+  int chunks = pick_chunks(grid_x, resident, rows, kv->lead + kv->out_delay,
+                           std::max(1, kv->trip));
   if (const char* forced = getenv("SODA_CUDA_CHUNKS"))
     chunks = std::max(1, std::min(rows, atoi(forced)));
   args.chunk_rows = (rows + chunks - 1) / chunks;

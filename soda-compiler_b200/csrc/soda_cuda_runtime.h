@@ -38,6 +38,8 @@ struct KernelVariant {
   int box_rows;                 // TMA box extent along the streamed dim
   int tiles_per_block;          // 2-D register kernels: strips (warps) per block
   int uses_tma;                 // the first kernel below needs tensor maps
+  int trip;                     // steps per trip of the streamed loop: a block
+                                // runs a whole number of trips
   const void* kernel_tma;       // __global__ void(StreamArgs): TMA / aligned
                                 // 128-bit input path
   const void* kernel_plain;     // same, any alignment

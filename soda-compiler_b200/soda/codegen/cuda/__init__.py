@@ -204,7 +204,11 @@ def _make_reg_schedule(program, depth, options, limit):
       except util.SemanticError as e:
         problem = problem or e
         continue
-      if total > limit:
+      # one block of 512 threads per SM is the design point whenever the
+      # histories are light: then the whole shared memory is the block's
+      roomy = (limit if history_registers(sched) > REG_HISTORY_3D // 2
+               else max(limit, SMEM_LIMIT - 2048))
+      if total > roomy:
         problem = problem or util.SemanticError(
             'depth %d with tile %s needs %d bytes of shared memory (limit '
             '%d)' % (depth, sched.tile, total, limit))
@@ -215,7 +219,16 @@ def _make_reg_schedule(program, depth, options, limit):
       break
   if best is None:
     raise problem
-  return best[1]
+  sched = best[1]
+  if not options.min_blocks:
+    # HBM-bound sweeps (one light stage) want two blocks per SM to hide the
+    # per-step barrier: cap the registers at 64 when shared memory allows it
+    # (heat3d depth 1: 613 -> 745 GCell/s; deeper chains spill and lose)
+    smem = kernel_reg_mod.Layout(sched).total + 1024
+    if (history_registers(sched) <= 16 and 2 * smem <= SMEM_LIMIT and
+        2 * sched.threads <= 2048):
+      sched.min_blocks = 2
+  return sched
 
 
 def make_schedule(program, depth, options, limit=SMEM_LIMIT):

@@ -189,9 +189,10 @@ class _Emitter:
       return 'uint32_t'
     return 'soda::f32x2' if self.sched.paired else node.c_type
 
-  def ring_slot(self, node, age):
-    depth = self.lay.ring_depth[node.index]
-    return '((ii - (%d)) & %d)' % (age, depth - 1)
+  def ring_slot(self, node, age, phase):
+    """Slot of the plane that is ``age`` steps old at step ``phase`` of a
+    trip: ring depths divide the trip, so this is a constant."""
+    return (phase - age) % self.lay.ring_depth[node.index]
 
   # ---- pieces ----------------------------------------------------------------
   def emit(self):
@@ -236,7 +237,7 @@ class _Emitter:
     self.emit_output_windows()
     # `steps` is a whole number of trips: the surplus steps compute rows no
     # block stores (beyond mine_hi) from rows that read as 0 or as real data
-    trip = lay.box_rows if self.flat else self.U
+    trip = lay.box_rows if self.flat else sched.trip
     if self.flat:
       p.println('for (int i = 0, box = 0; i < steps; i += %d, ++box)' % trip)
     else:
@@ -279,7 +280,7 @@ class _Emitter:
     p.println('const int r1 = min(a.row_end, r0 + a.chunk_rows);')
     p.println('const int base = r0 - %d;   // streamed coordinate of step 0' %
               sched.lead)
-    trip = sched.flat_box if self.flat else self.U
+    trip = sched.flat_box if self.flat else sched.trip
     p.println('// steps to run: (r1 - r0) + %d, rounded up to whole trips of '
               'the streamed loop' % (sched.lead + sched.out_delay))
     p.println('const int steps = ((r1 - r0) + %d) / %d * %d;' % (
@@ -523,18 +524,17 @@ class _Emitter:
     p.un_scope()
 
   # ---- 3-D input path: TMA into a shared ring --------------------------------
-  def tma_issue(self, rel_code):
+  def tma_issue(self, rel_code, slot):
+    """Request plane ``base + rel`` of every input into ring slot ``slot``."""
     p, lay, s = self.p, self.lay, self.s
-    p.println('uint64_t* const bar = &bars[(%s) & %d];' % (rel_code,
-                                                           self.DIN - 1))
+    p.println('uint64_t* const bar = &bars[%d];' % slot)
     p.println('soda::mbar_expect_tx(bar, %d);' % sum(lay.plane_bytes.values()))
     for node in lay.loaded_inputs:
       coords = ['org%d' % d for d in range(s)] + ['base + (%s)' % rel_code]
-      p.println('soda::tma_load(ring_%s + ((%s) & %d) * %d, &a.in_map[%d], '
-                'bar, %s);' % (node.ident, rel_code, self.DIN - 1, self.PLANE,
-                               node.input_index, ', '.join(coords)))
+      p.println('soda::tma_load(ring_%s + %d, &a.in_map[%d], bar, %s);' % (
+          node.ident, slot * self.PLANE, node.input_index, ', '.join(coords)))
 
-  def plain_load(self, rel_code):
+  def plain_load(self, rel_code, slot):
     p, lay, s, V = self.p, self.lay, self.s, self.V
     p.println('const int lrow = base + (%s);' % rel_code)
     p.println('const bool lrow_in = lrow >= 0 && lrow < a.dims[%d];' % s)
@@ -562,9 +562,8 @@ class _Emitter:
       p.println('  t[k] = (in && gx[j] + k >= 0 && gx[j] + k < a.dims[0]) ? '
                 'src[k] : %s(0);' % node.c_type)
       p.un_scope()
-      p.println('soda::st_pack<%s, %d>(ring_%s + ((%s) & %d) * %d + pos[j], '
-                't);' % (node.c_type, V, node.ident, rel_code, self.DIN - 1,
-                         self.PLANE))
+      p.println('soda::st_pack<%s, %d>(ring_%s + %d + pos[j], t);' % (
+          node.c_type, V, node.ident, slot * self.PLANE))
       p.un_scope()
 
   def emit_tma_prologue(self):
@@ -584,16 +583,17 @@ class _Emitter:
     p.println('__syncthreads();')
     p.println('if (tid == 0)')
     p.do_scope()
-    p.println('for (int rel = 0; rel < %d && rel < steps; ++rel)' % self.P)
-    p.do_scope()
-    self.tma_issue('rel')
-    p.un_scope()
+    for rel in range(self.P):
+      p.println('if (%d < steps)' % rel)
+      p.do_scope()
+      self.tma_issue(str(rel), rel % self.DIN)
+      p.un_scope()
     p.un_scope()
     p.un_scope()
     p.println('else')
     p.do_scope()
     p.do_scope()
-    self.plain_load('0')
+    self.plain_load('0', 0)
     p.un_scope()
     p.println('__syncthreads();')
     p.un_scope()
@@ -609,10 +609,11 @@ class _Emitter:
       p.do_scope()
       p.println('if (tid == 0 && ii + %d < steps)' % self.P)
       p.do_scope()
-      self.tma_issue('ii + %d' % self.P)
+      self.tma_issue('ii + %d' % self.P, (phase + self.P) % self.DIN)
       p.un_scope()
-      p.println('soda::mbar_wait(&bars[ii & %d], (ii >> %d) & 1);' % (
-          self.DIN - 1, _log2(self.DIN)))
+      # slot `phase mod DIN` is on its (i / DIN + phase / DIN)-th plane
+      p.println('soda::mbar_wait(&bars[%d], (i / %d + %d) & 1);' % (
+          phase % self.DIN, self.DIN, phase // self.DIN))
       p.un_scope()
       for node in lay.loaded_inputs:
         if node.hist_oldest is None:
@@ -622,17 +623,17 @@ class _Emitter:
         if self.loose[node.index]:
           p.do_scope()
           p.println('%s t[%d];' % (node.c_type, V))
-          p.println('soda::ld_pack<%s, %d>(t, ring_%s + %s * %d + pos[j]);' % (
-              node.c_type, V, node.ident, self.ring_slot(node, 0), self.PLANE))
+          p.println('soda::ld_pack<%s, %d>(t, ring_%s + %d + pos[j]);' % (
+              node.c_type, V, node.ident,
+              self.ring_slot(node, 0, phase) * self.PLANE))
           p.println('#pragma unroll')
           p.println('for (int k = 0; k < %d; ++k) %s[j][k] = t[k];' % (
               V, self.hist(node, phase, 0)))
           p.un_scope()
         else:
-          p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %s * %d + '
-                    'pos[j]);' % (node.c_type, V, self.hist(node, phase, 0),
-                                  node.ident, self.ring_slot(node, 0),
-                                  self.PLANE))
+          p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %d + pos[j]);'
+                    % (node.c_type, V, self.hist(node, phase, 0), node.ident,
+                       self.ring_slot(node, 0, phase) * self.PLANE))
     self.shuffled = {}     # (node index, age, element) -> variable, this step
     for node in sched.stage_nodes:
       self.emit_stage(node, phase)
@@ -640,7 +641,7 @@ class _Emitter:
       if lay.loaded_inputs:
         p.println('if (!kTma && ii + 1 < steps)')
         p.do_scope()
-        self.plain_load('ii + 1')
+        self.plain_load('ii + 1', (phase + 1) % self.DIN)
         p.un_scope()
       p.println('__syncthreads();')
 
@@ -702,9 +703,9 @@ class _Emitter:
       used = sorted({k + dx for dx in dxs for k in range(V)})
       inplane = sum(rest[d - 1] * sched.plane_pitch(d) for d in range(1, s))
       age = node.delay - rest[s - 1]
-      p.println('const %s* const s%d = ring_%s + %s * %d + pos[j] + (%d);' % (
-          parent.c_type, g, parent.ident, self.ring_slot(parent, age),
-          self.PLANE, inplane))
+      p.println('const %s* const s%d = ring_%s + pos[j] + (%d);' % (
+          parent.c_type, g, parent.ident,
+          self.ring_slot(parent, age, phase) * self.PLANE + inplane))
       p.println('%s w%d[%d];' % (parent.c_type, g, V + xhi - xlo))
       inside = [c for c in used if 0 <= c < V]
       if len(inside) >= 2 and xlo <= 0 <= xhi:
@@ -763,9 +764,9 @@ class _Emitter:
         p.println('#pragma unroll')
         p.println('for (int k = 0; k < %d; ++k) narrow[k] = static_cast<%s>('
                   '%s[k]);' % (V, node.c_type, target))
-      p.println('soda::st_pack<%s, %d>(ring_%s + %s * %d + pos[j], %s);' % (
-          node.c_type, V, node.ident, self.ring_slot(node, node.delay),
-          self.PLANE, plane))
+      p.println('soda::st_pack<%s, %d>(ring_%s + %d + pos[j], %s);' % (
+          node.c_type, V, node.ident,
+          self.ring_slot(node, node.delay, phase) * self.PLANE, plane))
     if node.output_index is not None and sched.paired:
       # lane A's result (iteration depth/2 - 1) feeds lane B one step later
       feeds = sched.inputs[node.output_index]

@@ -582,16 +582,38 @@ class RegSchedule(Schedule):
       # registers hold the rows of age node.delay .. hist_oldest
       node.hist_oldest = max(reg_ages) if reg_ages else None
       node.hist_newest = node.delay
+      # planes a shared ring must hold (rounded to a usable depth below)
       if node.is_input and self.input_in_smem:
-        node.ring_depth = (_pow2(max(smem_ages + [0]) + self.prefetch + 1)
+        node.ring_depth = (max(smem_ages + [0]) + self.prefetch + 1
                            if node.consumers else 0)
       elif smem_ages:
-        node.ring_depth = _pow2(max(smem_ages) - node.delay + 1)
+        node.ring_depth = max(smem_ages) - node.delay + 1
       else:
         node.ring_depth = 0
       if reg_ages:
         spans.append(node.hist_oldest - node.hist_newest + 1)
     self.period = max(spans)
+    # One trip of the streamed loop is `trip` steps, fully unrolled: a whole
+    # number of history periods, and a multiple of every ring depth, so that
+    # register slots AND shared-memory ring slots are compile-time constants
+    # (no per-step address arithmetic).  All input rings share one depth (one
+    # mbarrier per slot covers every input).
+    needs = [n.ring_depth for n in self.nodes if n.ring_depth]
+    self.trip = self.period
+    while needs and self.trip < max(needs):
+      self.trip += self.period
+    in_need = max([n.ring_depth for n in self.inputs] + [0])
+    for node in self.nodes:
+      if node.ring_depth:
+        need = in_need if node.is_input else node.ring_depth
+        node.ring_depth = min(d for d in range(need, self.trip + 1)
+                              if self.trip % d == 0)
+    if in_need and self.input_in_smem:
+      # slots the rounding added are used: request further ahead, keeping one
+      # slot of slack (heat3d depth 2, ring of 6: 2 ahead 1122, 3 ahead 1161,
+      # 4 ahead 1124 GCell/s)
+      depth = max(n.ring_depth for n in self.inputs)
+      self.prefetch = max(self.prefetch, self.prefetch + depth - in_need - 1)
 
   def _measure_halos(self):
     super()._measure_halos()

@@ -76,7 +76,8 @@ def main():
         ['cuobjdump', '-res-usage', path], stdout=subprocess.PIPE, text=True,
         check=False).stdout.split(want)[1]) if want else None
     count, mix = loop_stats(body)
-    period = getattr(sched, 'period', 1)
+    period = (getattr(sched, 'flat_box', 0) or getattr(sched, 'trip', 0) or
+              getattr(sched, 'period', 1))
     cells = period * sched.vec * sched.vecs_per_thread * sched.depth
     print('%-34s loop %5d inst / %4d cell updates = %6.2f per update  '
           '(fma %d alu %d mem %d ctl %d mufu %d)  regs %s' % (
