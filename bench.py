@@ -7,8 +7,10 @@ Workload (BASELINE.json configs[1]): jacobi2d, float32, 16384 x 16384,
 iterate 64.  One "step" is one complete run of the program: 64 iterations
 over the whole grid = 1.718e10 cell updates.  With N > 1 GPUs (launched by
 torch.distributed.run, one process per GPU) every rank owns a 16384-row slab
-of a 16384 x (16384 N) grid and exchanges halo rows over NCCL after every
-temporally blocked launch: weak scaling, value = all ranks' cell updates / s.
+of a 16384 x (16384 N) grid; after every temporally blocked launch its face
+rows are copied into the neighbours' ghost rows (peer-mapped memory over
+NVLink, copy engine + stream flags; soda/cuda_slab.py) while the interior is
+computed: weak scaling, value = all ranks' cell updates / s.
 
 What is timed
   value     inputs resident in HBM, CUDA events around K steps on the launch
@@ -86,16 +88,21 @@ class ClockSampler:
     except Exception:   # pylint: disable=broad-except
       self._nvml = None
 
+  def begin(self):
+    """Start of the timed region: forget what was sampled before."""
+    self.clocks, self.masks = [], 0
+
   def _poll(self):
     nv = self._nvml
     while not self._stop.is_set():
       try:
-        self.clocks.append(nv.nvmlDeviceGetClockInfo(self._handle,
-                                                     nv.NVML_CLOCK_SM))
-        self.masks |= nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        clock = nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)
+        mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._handle)
+        self.clocks.append(clock)
+        self.masks |= mask
       except Exception:   # pylint: disable=broad-except
         break
-      time.sleep(0.002)
+      time.sleep(float(os.environ.get('SODA_BENCH_CLOCK_PERIOD', '0.002')))
 
   def _smi_once(self):
     query = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
@@ -178,8 +185,10 @@ def workload_config(n_gpus):
                       'configs[1]); per GPU' % (d0, d1, WORKLOAD['iterate']),
           'global_grid': [d0, d1 * n_gpus], 'iterate': WORKLOAD['iterate'],
           'partition': 'single GPU' if n_gpus == 1 else
-                       '%d slabs along the streamed dimension, NCCL halo '
-                       'exchange per launch' % n_gpus,
+                       '%d slabs along the streamed dimension; per launch '
+                       'the face rows go to the neighbours\' ghost rows by '
+                       'copy engine over NVLink (peer-mapped memory + '
+                       'stream flags)' % n_gpus,
           'l2': 'inputs (1.07 GB per GPU) exceed the 126 MB L2; no flush'}
 
 
@@ -257,8 +266,12 @@ def main():
   # ---- device-resident timing ------------------------------------------------
   for _ in range(args.warmup):
     step()
-  barrier()
+  # NVML is initialised BEFORE the barrier: it takes milliseconds, and a rank
+  # that enters the timed region late holds its neighbours up by as much
   sampler = ClockSampler(local_rank) if rank == 0 else None
+  barrier()
+  if sampler:
+    sampler.begin()
   start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
   start.record()
   for _ in range(args.steps):

@@ -113,6 +113,31 @@ int soda_cuda_launch(int depth, const void* const* inputs,
 /* Fills up to `max` compiled depths (decreasing); returns how many exist. */
 int soda_cuda_depths(int32_t* depths, int max);
 
+/* Stream-ordered 32-bit flags in device memory (cuStreamWriteValue32 /
+ * cuStreamWaitValue32 with CU_STREAM_WAIT_VALUE_GEQ): executed by the GPU's
+ * front end, no SM needed, so a neighbour's halo planes can be announced and
+ * awaited while a launch occupies every SM.  `flag` is a 4-byte aligned
+ * device address, local or peer-mapped (CUDA IPC).  Used by the multi-GPU
+ * slab runner (soda/cuda_slab.py); no counterpart in the reference, which has
+ * no multi-device support. */
+int soda_cuda_flag_write(void* flag, uint32_t value, void* stream);
+int soda_cuda_flag_wait_geq(void* flag, uint32_t value, void* stream);
+
+/* Peer mapping of another process's device arrays (one process per GPU).
+ * soda_cuda_ipc_export: CUDA IPC handle (64 bytes) of the allocation that
+ * holds `ptr`, and the offset of `ptr` in it.  soda_cuda_ipc_open: maps that
+ * allocation into the CALLER's context on its own current device (peer access
+ * over NVLink) and returns its base address there; this process never creates
+ * a context on the neighbour's GPU, which would time-slice with the
+ * neighbour's kernels.  soda_cuda_copy_async: copy-engine transfer between
+ * any two device addresses, enqueued on `stream`. */
+int soda_cuda_ipc_export(const void* ptr, unsigned char handle[64],
+                         uint64_t* offset);
+int soda_cuda_ipc_open(const unsigned char handle[64], void** base);
+int soda_cuda_ipc_close(void* base);
+int soda_cuda_copy_async(void* dst, const void* src, uint64_t bytes,
+                         void* stream);
+
 const soda_cuda_stats_t* soda_cuda_last_stats(void);
 /* Releases cached device buffers and streams. */
 void soda_cuda_release(void);

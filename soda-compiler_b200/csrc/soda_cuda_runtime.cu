@@ -29,11 +29,18 @@ using EncodeTiledFn = CUresult (*)(
     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
     CUtensorMapFloatOOBfill);
 
+using StreamValueFn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t,
+                                   unsigned int);
+using AddressRangeFn = CUresult (*)(CUdeviceptr*, size_t*, CUdeviceptr);
+
 struct Device {
   bool ready = false;
   int error = kNoDeviceInterface;
   int sm_count = 0;
   EncodeTiledFn encode = nullptr;
+  StreamValueFn write_value = nullptr;
+  StreamValueFn wait_value = nullptr;
+  AddressRangeFn address_range = nullptr;
 };
 
 std::mutex g_mutex;
@@ -75,6 +82,18 @@ int ensure_device() {
                                      cudaEnableDefault, &qres),
              kNoDeviceInterface);
   g_device.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  SODA_CHECK(cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn,
+                                     cudaEnableDefault, &qres),
+             kNoDeviceInterface);
+  g_device.write_value = reinterpret_cast<StreamValueFn>(fn);
+  SODA_CHECK(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn,
+                                     cudaEnableDefault, &qres),
+             kNoDeviceInterface);
+  g_device.wait_value = reinterpret_cast<StreamValueFn>(fn);
+  SODA_CHECK(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn,
+                                     cudaEnableDefault, &qres),
+             kNoDeviceInterface);
+  g_device.address_range = reinterpret_cast<AddressRangeFn>(fn);
   for (auto& ev : g_ev) SODA_CHECK(cudaEventCreate(&ev), kNoDeviceInterface);
   g_ev_ready = true;
   g_device.ready = true;
@@ -751,6 +770,73 @@ int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
     fprintf(stderr, "INFO: Kernel throughput: %lf pixel/ns\n",
             st->kernel_ms > 0 ? cells / (st->kernel_ms * 1e6) : 0.0);
   }
+  return kSuccess;
+}
+
+int flag_write(void* flag, uint32_t value, cudaStream_t stream) {
+  if (int code = ensure_device()) return code;
+  const CUresult res = g_device.write_value(
+      stream, reinterpret_cast<CUdeviceptr>(flag), value,
+      CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (res != CUDA_SUCCESS) {
+    fprintf(stderr, "ERROR: cuStreamWriteValue32 failed (%d)\n",
+            static_cast<int>(res));
+    return kDeviceRunFailed;
+  }
+  return kSuccess;
+}
+
+int flag_wait_geq(void* flag, uint32_t value, cudaStream_t stream) {
+  if (int code = ensure_device()) return code;
+  const CUresult res = g_device.wait_value(
+      stream, reinterpret_cast<CUdeviceptr>(flag), value,
+      CU_STREAM_WAIT_VALUE_GEQ);
+  if (res != CUDA_SUCCESS) {
+    fprintf(stderr, "ERROR: cuStreamWaitValue32 failed (%d)\n",
+            static_cast<int>(res));
+    return kDeviceRunFailed;
+  }
+  return kSuccess;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are 64 bytes");
+
+int ipc_export(const void* ptr, unsigned char handle[64], uint64_t* offset) {
+  if (int code = ensure_device()) return code;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (g_device.address_range(&base, &size,
+                             reinterpret_cast<CUdeviceptr>(ptr)) !=
+      CUDA_SUCCESS) {
+    fprintf(stderr, "ERROR: %p is not a device allocation\n", ptr);
+    return kDeviceRunFailed;
+  }
+  cudaIpcMemHandle_t h;
+  SODA_CHECK(cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)),
+             kDeviceRunFailed);
+  memcpy(handle, &h, 64);
+  *offset = reinterpret_cast<CUdeviceptr>(ptr) - base;
+  return kSuccess;
+}
+
+int ipc_open(const unsigned char handle[64], void** base) {
+  if (int code = ensure_device()) return code;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  SODA_CHECK(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess),
+             kDeviceRunFailed);
+  return kSuccess;
+}
+
+int ipc_close(void* base) {
+  SODA_CHECK(cudaIpcCloseMemHandle(base), kDeviceRunFailed);
+  return kSuccess;
+}
+
+int copy_async(void* dst, const void* src, uint64_t bytes,
+               cudaStream_t stream) {
+  SODA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream),
+             kDeviceRunFailed);
   return kSuccess;
 }
 

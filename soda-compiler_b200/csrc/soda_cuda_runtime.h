@@ -104,6 +104,18 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
            int row_end, const int32_t* valid_lo, const int32_t* valid_hi,
            cudaStream_t stream);
 
+// Stream-ordered flag in device memory (local or peer-mapped): written and
+// awaited by the GPU front end, not by a kernel.
+int flag_write(void* flag, uint32_t value, cudaStream_t stream);
+int flag_wait_geq(void* flag, uint32_t value, cudaStream_t stream);
+
+// CUDA IPC: export the allocation holding `ptr`; map a neighbour's allocation
+// into this process's context on its own device; copy-engine transfers.
+int ipc_export(const void* ptr, unsigned char handle[64], uint64_t* offset);
+int ipc_open(const unsigned char handle[64], void** base);
+int ipc_close(void* base);
+int copy_async(void* dst, const void* src, uint64_t bytes, cudaStream_t stream);
+
 const soda_cuda_stats_t* last_stats();
 
 // Frees the cached device buffers.

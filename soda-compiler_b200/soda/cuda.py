@@ -175,6 +175,15 @@ class Library:
         ('soda_cuda_launch', c_int,
          [c_int, voidpp, voidpp, i32p, c_int, c_int, i32p, i32p, c_void_p]),
         ('soda_cuda_depths', c_int, [i32p, c_int]),
+        ('soda_cuda_flag_write', c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
+        ('soda_cuda_flag_wait_geq', c_int,
+         [c_void_p, ctypes.c_uint32, c_void_p]),
+        ('soda_cuda_ipc_export', c_int,
+         [c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]),
+        ('soda_cuda_ipc_open', c_int, [ctypes.c_char_p, voidpp]),
+        ('soda_cuda_ipc_close', c_int, [c_void_p]),
+        ('soda_cuda_copy_async', c_int,
+         [c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
         ('soda_cuda_last_stats', ctypes.POINTER(Stats), []),
         ('soda_cuda_release', None, []),
     ):
@@ -307,6 +316,42 @@ class Library:
         (ctypes.c_int32 * 4)(*dims), iterate, stream)
     if code:
       raise CudaError('soda_cuda_run_device(%s)' % self.app_name, code)
+
+  def ipc_export(self, address):
+    """``(handle bytes, offset)`` of the device allocation holding
+    ``address``, for another process to map (see soda_cuda_ipc_export)."""
+    handle = ctypes.create_string_buffer(64)
+    offset = ctypes.c_uint64()
+    code = self._lib.soda_cuda_ipc_export(address, handle,
+                                          ctypes.byref(offset))
+    if code:
+      raise CudaError('soda_cuda_ipc_export', code)
+    return handle.raw, offset.value
+
+  def ipc_open(self, handle):
+    """Base address, in this process, of a neighbour's exported allocation."""
+    base = ctypes.c_void_p()
+    code = self._lib.soda_cuda_ipc_open(handle, ctypes.byref(base))
+    if code:
+      raise CudaError('soda_cuda_ipc_open', code)
+    return base.value
+
+  def copy_async(self, dst, src, nbytes, stream=None):
+    code = self._lib.soda_cuda_copy_async(dst, src, nbytes, stream)
+    if code:
+      raise CudaError('soda_cuda_copy_async', code)
+
+  def flag_write(self, address, value, stream=None):
+    """Stream-ordered store of a 32-bit flag (see soda_cuda_flag_write)."""
+    code = self._lib.soda_cuda_flag_write(address, value, stream)
+    if code:
+      raise CudaError('soda_cuda_flag_write', code)
+
+  def flag_wait_geq(self, address, value, stream=None):
+    """The stream waits until the 32-bit flag is >= ``value``."""
+    code = self._lib.soda_cuda_flag_wait_geq(address, value, stream)
+    if code:
+      raise CudaError('soda_cuda_flag_wait_geq', code)
 
   def launch(self, depth, inputs, outputs, dims, row_begin, row_end,
              valid_lo, valid_hi, stream=None):

@@ -17,9 +17,31 @@ Ranks at the ends of the grid have no neighbour there: the kernel reads
 outside the local array as 0, exactly as a single GPU reads outside the grid,
 so the sharded result is bit-identical to the single-GPU result (tested).
 
+Two ways to move the face planes.
+
+``p2p`` (default on GPUs)  The interior launch is sized to fill every SM for
+    its whole duration, so an NCCL send/recv *kernel* queued next to it only
+    gets an SM when the interior drains: the exchange ends up serialised
+    after the compute it was meant to hide behind (measured: 2 GPUs at 86 %
+    of 2 x one GPU).  Here the neighbours' arrays are mapped into this
+    process (CUDA IPC) and the face planes are written straight into the
+    neighbour's ghost rows by the **copy engine** (peer-to-peer over
+    NVLink), followed by a stream-ordered 32-bit flag
+    (cuStreamWriteValue32); the neighbour's next launch waits on the flag
+    (cuStreamWaitValue32).  Nothing on this path needs an SM.  Output arrays
+    rotate through three buffers, which is what makes writing into a
+    neighbour's ghost rows safe without a credit message: the buffer written
+    in launch n was last read in launch n - 2, and a rank cannot be two
+    launches ahead of the neighbour it waits on.  Across ``run()`` calls a
+    second flag says "previous run finished".
+``collective``  torch.distributed send/recv (NCCL on GPUs, gloo in the CPU
+    tests), ping-pong buffers.  Set SODA_CUDA_SLAB_EXCHANGE=collective.
+
 The reference has no multi-device support; this is the part of
 the backend that is new functionality rather than a replacement.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -50,7 +72,7 @@ class SlabRunner:
   """
 
   def __init__(self, library, global_dims, rank, world, feedback=None,
-               group=None, device=None, compute=None):
+               group=None, device=None, compute=None, exchange=None):
     self.library = library
     self.global_dims = tuple(global_dims)
     self.rank, self.world, self.group = rank, world, group
@@ -88,15 +110,136 @@ class SlabRunner:
         np.empty(0, soda_cuda.NUMPY_TYPES[t])).dtype
     self.inputs = [torch.zeros(shape, dtype=dtype(t), device=self.device)
                    for _, t in library.inputs]
-    # two sets of output-typed arrays to ping-pong between launches
+    if exchange is None:
+      exchange = os.environ.get('SODA_CUDA_SLAB_EXCHANGE') or (
+          'p2p' if self.on_gpu and compute is None and world > 1
+          else 'collective')
+    if exchange not in ('p2p', 'collective'):
+      raise ValueError('exchange must be `p2p` or `collective`')
+    self.exchange = exchange
+    # sets of output-typed arrays the launches rotate through
     self.buffers = [[torch.zeros(shape, dtype=dtype(t), device=self.device)
-                     for _, t in library.outputs] for _ in range(2)]
+                     for _, t in library.outputs]
+                    for _ in range(3 if exchange == 'p2p' else 2)]
     self.current = list(self.inputs)     # what the next launch reads
     self.outputs = None
     if self.on_gpu:
       self.main = torch.cuda.current_stream(self.device)
       self.comm = torch.cuda.Stream(self.device)
     self.launch_count = 0
+    if exchange == 'p2p':
+      self._setup_p2p()
+
+  # ---- peer-to-peer exchange ------------------------------------------------
+  def _setup_p2p(self):
+    """Map the neighbours' output arrays and flags into this process: CUDA
+    IPC handles opened in MY context on MY device (soda_cuda_ipc_open).  The
+    process never touches the neighbour's GPU through a context of its own —
+    a second context there time-slices with the neighbour's kernels (measured
+    with torch's tensor sharing, which does create one: 2.3x slower)."""
+    lib = self.library
+    self.fed_outputs = sorted(set(self.feedback.values()))
+    # flags: 0 ghosts from below landed, 1 from above, 2/3 the neighbour
+    # below/above finished its previous run, 7 scratch
+    self.flags = torch.zeros(8, dtype=torch.int32, device=self.device)
+    torch.cuda.synchronize(self.device)
+    mine = {'flags': lib.ipc_export(self.flags.data_ptr()),
+            'buffers': [[lib.ipc_export(bufs[k].data_ptr())
+                         for k in self.fed_outputs] for bufs in self.buffers]}
+    everyone = [None] * self.world
+    dist.all_gather_object(everyone, mine, group=self.group)
+    self.peers = {}
+    opened = {}
+
+    def address(exported):
+      handle, offset = exported
+      if handle not in opened:       # an allocation is opened once
+        opened[handle] = lib.ipc_open(handle)
+      return opened[handle] + offset
+    rows = self.global_dims[-1]
+    self.plane_bytes = [self.buffers[0][k][0].numel() *
+                        self.buffers[0][k].element_size()
+                        for k in self.fed_outputs]
+    for side, q in ((0, self.rank - 1), (1, self.rank + 1)):
+      if not 0 <= q < self.world:
+        continue
+      begin, end = partition(rows, self.world)[q]
+      first = self.reach_lo if q > 0 else 0       # its local index of `begin`
+      self.peers[side] = {
+          'flags': address(everyone[q]['flags']),
+          'buffers': [[address(t) for t in bufs]
+                      for bufs in everyone[q]['buffers']],
+          # its ghost rows that mirror my face: above its slab if it is below
+          # me, below its slab if it is above me
+          'ghost': ((first + end - begin, first + end - begin + self.reach_hi)
+                    if side == 0 else (first - self.reach_lo, first)),
+      }
+    # a flag in a neighbour's memory is written by cuStreamWriteValue32 where
+    # the driver accepts a peer-mapped address, else by a 4-byte peer copy of
+    # a locally written value (both stream-ordered, neither needs an SM)
+    self.stage = torch.zeros(2, dtype=torch.int32, device=self.device)
+    self.flag_by_copy = False
+    try:
+      for peer in self.peers.values():
+        lib.flag_write(peer['flags'] + 4 * 7, 1, self.comm.cuda_stream)
+      self.comm.synchronize()
+    except Exception:   # pylint: disable=broad-except
+      self.flag_by_copy = True
+    dist.barrier(group=self.group)
+    self.tick = 0          # exchanges so far (same on every rank)
+    self.run_index = 0
+    self.push_done = None
+
+  def _raise_flag(self, side, index, value, stream):
+    """Stream-ordered ``peer.flags[index] = value``."""
+    lib, target = self.library, self.peers[side]['flags'] + 4 * index
+    if not self.flag_by_copy:
+      lib.flag_write(target, value, stream.cuda_stream)
+      return
+    source = self.stage.data_ptr() + 4 * side
+    lib.flag_write(source, value, stream.cuda_stream)
+    lib.copy_async(target, source, 4, stream.cuda_stream)
+
+  def _push_faces(self, target, bset, first_pass):
+    """On the communication stream: copy my face planes into the neighbours'
+    ghost rows of the same buffer set, then raise their `landed` flag."""
+    lib = self.library
+    a = self.begin - self.local_begin
+    b = a + (self.end - self.begin)
+    stream = self.comm.cuda_stream
+    self.tick += 1
+    for side, peer in self.peers.items():
+      if first_pass and self.run_index:
+        # the neighbour may still be reading this buffer set in its last run
+        lib.flag_wait_geq(self.flags.data_ptr() + 4 * (2 + side),
+                          self.run_index, stream)
+      face = (a, a + self.reach_hi) if side == 0 else (b - self.reach_lo, b)
+      g0, g1 = peer['ghost']
+      if g1 > g0:
+        for slot, out in enumerate(self.fed_outputs):
+          plane = self.plane_bytes[slot]
+          lib.copy_async(peer['buffers'][bset][slot] + g0 * plane,
+                         target[out].data_ptr() + face[0] * plane,
+                         (g1 - g0) * plane, stream)
+      # I am `above` my lower neighbour (its flag 1) and `below` my upper one
+      self._raise_flag(side, 1 - side, self.tick, self.comm)
+    self.push_done = self.comm.record_event()
+
+  def _await_ghosts(self):
+    """The next launches on the main stream need the ghosts of exchange
+    number ``self.tick``."""
+    stream = self.main.cuda_stream
+    for side in self.peers:
+      self.library.flag_wait_geq(self.flags.data_ptr() + 4 * side, self.tick,
+                                 stream)
+    if self.push_done is not None:
+      self.main.wait_event(self.push_done)   # my faces left before I rewrite
+
+  def _finish_run(self):
+    """Tell the neighbours this run no longer reads any buffer."""
+    self.run_index += 1
+    for side in self.peers:
+      self._raise_flag(side, 3 - side, self.run_index, self.main)
 
   # ---- data movement ----------------------------------------------------
   def owned(self, tensor):
@@ -178,13 +321,16 @@ class SlabRunner:
     b = a + (self.end - self.begin)
     current = list(self.inputs)
     pending = []
+    p2p = self.exchange == 'p2p'
     for n, depth in enumerate(depths):
       last = n + 1 == len(depths)
-      target = self.buffers[n % 2]
+      target = self.buffers[n % len(self.buffers)]
       lo, hi = (fin_lo, fin_hi) if last else (full_lo, full_hi)
       for req in pending:       # ghosts of `current` must have landed
         req.wait()
       pending = []
+      if p2p and n:
+        self._await_ghosts()
 
       def go(row_begin, row_end, current=current, target=target, lo=lo,
              hi=hi, depth=depth):
@@ -201,7 +347,12 @@ class SlabRunner:
         go(a, low_face)
         go(high_face, b)
         fed = [target[out] for out in self.feedback.values()]
-        if self.on_gpu:
+        if p2p:
+          faces_done = self.main.record_event()
+          with torch.cuda.stream(self.comm):
+            self.comm.wait_event(faces_done)
+            self._push_faces(target, n % len(self.buffers), n == 0)
+        elif self.on_gpu:
           faces_done = self.main.record_event()
           with torch.cuda.stream(self.comm):
             self.comm.wait_event(faces_done)
@@ -214,5 +365,7 @@ class SlabRunner:
         for inp, out in self.feedback.items():
           nxt[inp] = target[out]
         current = nxt
+    if p2p and self.world > 1:
+      self._finish_run()
     self.outputs = [self.owned(t) for t in target]
     return self.outputs

@@ -20,12 +20,18 @@ def _free_port():
     return sock.getsockname()[1]
 
 
+# program, iterate, backend options, global dims[, exchange]; the default
+# exchange on GPUs is `p2p` (copy engine into peer-mapped ghost rows + flags)
 CASES = [
     ('jacobi2d', 16, {'depth': 4}, (2048, 700)),
     ('jacobi2d', 7, {'depth': 4}, (1030, 333)),
+    ('jacobi2d', 40, {'depth': 8}, (2048, 600)),      # 5 launches, 3 buffers
     ('heat3d', 4, {'depth': 2}, (128, 64, 90)),
+    ('seidel2d', 6, {'depth': 2}, (1280, 400)),
     ('blur', 1, {}, (1037, 211)),
     ('denoise2d', 1, {}, (1024, 200)),
+    ('jacobi2d', 16, {'depth': 4}, (2048, 700), 'collective'),   # NCCL
+    ('heat3d', 4, {'depth': 2}, (128, 64, 90), 'collective'),
 ]
 
 
@@ -41,15 +47,17 @@ def _worker(rank, world, port, queue):
   try:
     from soda import cuda as soda_cuda, cuda_slab
     from soda.codegen import cuda as codegen
-    for index, (name, iterate, options, dims) in enumerate(CASES):
+    for index, (name, iterate, options, dims, *how) in enumerate(CASES):
       library = soda_cuda.compile_stencil(common.stencil(name, iterate),
                                           options=codegen.Options(**options))
       orc = common.oracle(name, iterate)
       full = common.random_inputs(orc, dims, seed=23)
-      runner = cuda_slab.SlabRunner(library, dims, rank, world)
+      runner = cuda_slab.SlabRunner(library, dims, rank, world,
+                                    exchange=how[0] if how else None)
+      assert runner.exchange == (how[0] if how else 'p2p')
       runner.load_local([torch.from_numpy(a[runner.begin:runner.end].copy()
                                           ).cuda() for a in full])
-      for _ in range(2):          # running twice must give the same answer
+      for _ in range(3):          # back-to-back runs, no barrier in between
         outs = runner.run(iterate)
       torch.cuda.synchronize()
       queue.put((index, rank, runner.begin, runner.end,
@@ -66,7 +74,7 @@ def test_sharded_equals_oracle():
   import torch.multiprocessing as mp
   from soda import cuda as soda_cuda
   from soda.codegen import cuda as codegen
-  for name, iterate, options, dims in CASES:
+  for name, iterate, options, dims, *_ in CASES:
     soda_cuda.build(common.stencil(name, iterate),
                     options=codegen.Options(**options))
   ctx = mp.get_context('spawn')
@@ -80,7 +88,7 @@ def test_sharded_equals_oracle():
   for proc in procs:
     proc.join(timeout=60)
     assert proc.exitcode == 0
-  for index, (name, iterate, options, dims) in enumerate(CASES):
+  for index, (name, iterate, options, dims, *_) in enumerate(CASES):
     orc = common.oracle(name, iterate)
     want = orc.run(common.random_inputs(orc, dims, seed=23))
     for k, expected in enumerate(want):

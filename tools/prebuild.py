@@ -48,7 +48,7 @@ def main():
       jobs.append((name, iterate, options))
     for name, iterate, _ in test_parity_gpu.REF_CASES:
       jobs.append((name, iterate, {}))
-    for name, iterate, options, _ in test_slab_gpu.CASES:
+    for name, iterate, options, *_ in test_slab_gpu.CASES:
       jobs.append((name, iterate, options))
     import test_types_gpu
     for name, _, options in test_types_gpu.CASES:
