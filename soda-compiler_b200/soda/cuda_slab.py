@@ -126,6 +126,7 @@ class SlabRunner:
     if self.on_gpu:
       self.main = torch.cuda.current_stream(self.device)
       self.comm = torch.cuda.Stream(self.device)
+      self.side = torch.cuda.Stream(self.device)
     self.launch_count = 0
     if exchange == 'p2p':
       self._setup_p2p()
@@ -344,8 +345,19 @@ class SlabRunner:
         low_face = min(b, a + self.reach_hi) if self.rank > 0 else a
         high_face = max(low_face, b - self.reach_lo) \
             if self.rank + 1 < self.world else b
-        go(a, low_face)
-        go(high_face, b)
+        if self.on_gpu and low_face > a and b > high_face:
+          # two faces (a rank with two neighbours): small launches, run them
+          # side by side instead of one after the other
+          begun = self.main.record_event()
+          with torch.cuda.stream(self.side):
+            self.side.wait_event(begun)
+            go(high_face, b)
+            high_done = self.side.record_event()
+          go(a, low_face)
+          self.main.wait_event(high_done)
+        else:
+          go(a, low_face)
+          go(high_face, b)
         fed = [target[out] for out in self.feedback.values()]
         if p2p:
           faces_done = self.main.record_event()
