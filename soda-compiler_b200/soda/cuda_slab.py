@@ -301,6 +301,23 @@ class SlabRunner:
       left -= fits[0]
     return depths
 
+  def valid_region(self, iterate):
+    """``[(lo, hi)]`` per dimension of the global grid after ``iterate``
+    iterations.  More iterations than the program was compiled for means
+    repeated application with the fed-back tensors (``u <- output``; the
+    reference refuses to iterate programs whose inputs and outputs differ,
+    src/soda/core.py:228-233, so its harness would be called once per
+    application): every application shrinks the region by its own window,
+    exactly as the golden loop bounds do (host.py:1082-1091)."""
+    if iterate <= self.library.iterate:
+      return self.library.valid_region(self.global_dims, iterate)
+    lo, hi = [0] * self.dim, [0] * self.dim
+    for depth in self.plan(iterate):
+      step_lo, step_hi = self.library.window(depth)
+      lo = [a + max(0, -b) for a, b in zip(lo, step_lo)]
+      hi = [a + max(0, b) for a, b in zip(hi, step_hi)]
+    return [(l, max(l, n - h)) for l, h, n in zip(lo, hi, self.global_dims)]
+
   def launches_per_run(self, iterate):
     faces = (1 if self.rank > 0 else 0) + (1 if self.rank + 1 < self.world
                                            else 0)
@@ -312,7 +329,7 @@ class SlabRunner:
     depths = self.plan(iterate)
     if len(depths) > 1 and not self.feedback:
       raise ValueError('iterations need outputs that feed the inputs')
-    region = self.library.valid_region(self.global_dims, iterate)
+    region = self.valid_region(iterate)
     full_lo, full_hi = [0] * self.dim, list(self.local_dims)
     fin_lo = [lo for lo, _ in region]
     fin_hi = [hi for _, hi in region]

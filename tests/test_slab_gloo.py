@@ -59,7 +59,8 @@ def _oracle_compute(name):
   return compute
 
 
-def _worker(rank, world, port, name, iterate, depths, dims, seed, queue):
+def _worker(rank, world, port, name, iterate, depths, dims, seed, queue,
+            feedback=None, times=None):
   os.environ['MASTER_ADDR'] = '127.0.0.1'
   os.environ['MASTER_PORT'] = str(port)
   dist.init_process_group('gloo', rank=rank, world_size=world)
@@ -69,10 +70,11 @@ def _worker(rank, world, port, name, iterate, depths, dims, seed, queue):
     orc = common.oracle(name, iterate)
     full = common.random_inputs(orc, dims, seed=seed)
     runner = cuda_slab.SlabRunner(library, dims, rank, world,
-                                  compute=_oracle_compute(name))
+                                  compute=_oracle_compute(name),
+                                  feedback=feedback)
     owned = [torch.from_numpy(a[runner.begin:runner.end].copy()) for a in full]
     runner.load_local(owned)
-    outs = runner.run(iterate)
+    outs = runner.run(times or iterate)
     queue.put((rank, runner.begin, runner.end,
                [o.numpy().copy() for o in outs]))
     dist.barrier()
@@ -110,6 +112,45 @@ def test_sharded_equals_single_process(name, iterate, depths, dims, world):
     for _, begin, end, outs in pieces:
       got[begin:end] = outs[k]
     common.assert_bit_exact(got, expected, '%s world %d' % (name, world))
+
+
+@pytest.mark.parametrize('name,times,dims,world', [
+    ('denoise2d', 3, (30, 41), 2),
+    ('denoise3d', 2, (13, 12, 25), 3),
+])
+def test_repeated_application_sharded(name, times, dims, world):
+  """BASELINE config 5 ("denoise3d iterate 16"): the reference refuses to
+  iterate a program with 2 inputs and 1 output (core.py:228-233), so the
+  program is applied `times` times with u <- output.  Sharded == the golden
+  loop called `times` times, on the region that survives every call."""
+  common.oracle(name, 1)
+  ctx = mp.get_context('spawn')
+  queue = ctx.Queue()
+  port = _free_port()
+  procs = [ctx.Process(target=_worker, args=(
+      rank, world, port, name, 1, (1,), dims, 29, queue, {1: 0}, times))
+           for rank in range(world)]
+  for proc in procs:
+    proc.start()
+  pieces = [queue.get(timeout=120) for _ in procs]
+  for proc in procs:
+    proc.join(timeout=60)
+    assert proc.exitcode == 0
+  orc = common.oracle(name, 1)
+  f, u = common.random_inputs(orc, dims, seed=29)
+  for _ in range(times):
+    u, = orc.run([f, u])
+  lo, hi = FakeLibrary(name, 1, (1,)).window(1)
+  keep = np.zeros(u.shape, dtype=bool)
+  keep[tuple(slice(-l * times, n - h * times) for l, h, n in
+             reversed(list(zip(lo, hi, dims))))] = True
+  expected = np.where(keep, u, 0).astype(u.dtype)
+  got = np.zeros_like(expected)
+  for _, begin, end, outs in pieces:
+    got[begin:end] = outs[0]
+  assert keep.sum() > 0
+  common.assert_bit_exact(got, expected, '%s x%d world %d' % (
+      name, times, world))
 
 
 def test_partition_and_refusals():

@@ -98,3 +98,29 @@ def test_sharded_equals_oracle():
           got[begin:end] = outs[k]
       common.assert_bit_exact(got, expected,
                               '%s on %d GPUs' % (name, world))
+
+
+@pytest.mark.parametrize('name,times,dims', [
+    ('denoise3d', 4, (96, 40, 33)),
+    ('denoise2d', 3, (1024, 70)),
+])
+def test_repeated_application_one_gpu(name, times, dims):
+  """BASELINE config 5 ("denoise3d iterate 16" is outside the reference,
+  core.py:228-233): the program applied `times` times with u <- output equals
+  the golden loop called `times` times, on the region every call keeps."""
+  from soda import cuda as soda_cuda, cuda_slab
+  library = soda_cuda.compile_stencil(common.stencil(name, 1))
+  orc = common.oracle(name, 1)
+  f, u = common.random_inputs(orc, dims, seed=31)
+  runner = cuda_slab.SlabRunner(library, dims, 0, 1, feedback={1: 0})
+  runner.load_local([torch.from_numpy(f).cuda(), torch.from_numpy(u).cuda()])
+  got = runner.run(times)[0].cpu().numpy()
+  for _ in range(times):
+    u, = orc.run([f, u])
+  lo, hi = library.window(1)
+  keep = np.zeros(u.shape, dtype=bool)
+  keep[tuple(slice(-l * times, n - h * times) for l, h, n in
+             reversed(list(zip(lo, hi, dims))))] = True
+  assert keep.sum() > 0
+  common.assert_bit_exact(got, np.where(keep, u, 0).astype(u.dtype),
+                          '%s x%d' % (name, times))

@@ -35,7 +35,13 @@ def main():
     import quick_bench
     for text in args:
       name, iterate, _, options = quick_bench.parse_case(text)
-      options.pop('e2e', None)
+      for key in ('e2e', 'weak', 'feed', 'exchange'):
+        options.pop(key, None)
+      try:
+        core.Stencil.from_file(os.path.join(
+            ROOT, 'benchmarks', name + '.soda'), iterate=iterate)
+      except Exception:   # pylint: disable=broad-except
+        iterate = 1       # applied `iterate` times by the caller (denoise)
       jobs.append((name, iterate, options))
   else:
     import test_parity_gpu

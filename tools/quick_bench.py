@@ -27,7 +27,8 @@ def parse_case(text):
   for item in parts[3:]:
     key, value = item.split('=')
     options[key] = ([int(v) for v in value.split('x')] if key == 'tile'
-                    else value if key == 'style' else int(value))
+                    else value if key in ('style', 'feed', 'exchange')
+                    else int(value))
   return name, iterate, dims, options
 
 
