@@ -110,6 +110,20 @@ int soda_cuda_launch(int depth, const void* const* inputs,
                      void* const* outputs, const int32_t* dims, int row_begin,
                      int row_end, const int32_t* valid_lo,
                      const int32_t* valid_hi, void* stream);
+/* The same launch with the rows per thread block along the streamed
+ * dimension given (`chunk_rows` > 0) instead of chosen.  A caller that splits
+ * a slab into several launches (faces first, see soda/cuda_slab.py) passes the
+ * value soda_cuda_chunk_rows returns for the whole slab, so that the pieces
+ * together are exactly the blocks of the one-launch decomposition: no row is
+ * led into twice. */
+int soda_cuda_launch_chunked(int depth, const void* const* inputs,
+                             void* const* outputs, const int32_t* dims,
+                             int row_begin, int row_end,
+                             const int32_t* valid_lo, const int32_t* valid_hi,
+                             int chunk_rows, void* stream);
+/* Rows per block soda_cuda_launch picks for `rows` streamed rows of a grid of
+ * extents `dims` (whole waves of resident blocks on this device); < 0: error. */
+int soda_cuda_chunk_rows(int depth, const int32_t* dims, int rows);
 /* Fills up to `max` compiled depths (decreasing); returns how many exist. */
 int soda_cuda_depths(int32_t* depths, int max);
 

@@ -222,12 +222,57 @@ int plan_depths(const ProgramDesc& prog, int iterate, std::vector<int>* depths) 
   return kSuccess;
 }
 
+// Rows per block along the streamed dimension for a launch over `rows` rows.
+int choose_chunk_rows(const ProgramDesc& prog, const KernelVariant* kv,
+                      const void* fn, const int32_t* dims, int rows,
+                      long long* grid_x_out, int* per_sm_out) {
+  SODA_CHECK(cudaFuncSetAttribute(fn,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kv->smem_bytes),
+             kDeviceRunFailed);
+  int per_sm = 0;
+  SODA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                 &per_sm, fn, kv->threads, kv->smem_bytes),
+             kDeviceRunFailed);
+  if (per_sm < 1) {
+    fprintf(stderr, "ERROR: kernel of %s does not fit on an SM (%d B smem)\n",
+            prog.app_name, kv->smem_bytes);
+    return kDeviceRunFailed;
+  }
+  long long tile_blocks = 1;
+  for (int d = 0; d + 1 < prog.dim; ++d)
+    tile_blocks *= (dims[d] + kv->own[d] - 1) / kv->own[d];
+  const long long resident =
+      static_cast<long long>(per_sm) * g_device.sm_count;
+  // 2-D register kernels pack `tiles_per_block` independent strips in a block
+  const int per_block = std::max(1, kv->tiles_per_block);
+  const long long grid_x = (tile_blocks + per_block - 1) / per_block;
+  int chunks = pick_chunks(grid_x, resident, rows, kv->lead + kv->out_delay,
+                           std::max(1, kv->trip));
+  if (const char* forced = getenv("SODA_CUDA_CHUNKS"))
+    chunks = std::max(1, std::min(rows, atoi(forced)));
+  if (grid_x_out != nullptr) *grid_x_out = grid_x;
+  if (per_sm_out != nullptr) *per_sm_out = per_sm;
+  return (rows + chunks - 1) / chunks;
+}
+
 }  // namespace
+
+int chunk_rows(const ProgramDesc& prog, int depth, const int32_t* dims,
+               int rows) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  int rc = ensure_device();
+  if (rc != kSuccess) return rc;
+  const KernelVariant* kv = find_variant(prog, depth);
+  if (kv == nullptr || rows < 1) return kInternalError;
+  return choose_chunk_rows(prog, kv, kv->kernel_tma, dims, rows, nullptr,
+                           nullptr);
+}
 
 int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
            void* const* outputs, const int32_t* dims, int row_begin,
            int row_end, const int32_t* valid_lo, const int32_t* valid_hi,
-           cudaStream_t stream) {
+           cudaStream_t stream, int forced_chunk_rows) {
   std::lock_guard<std::mutex> lock(g_mutex);
   int rc = ensure_device();
   if (rc != kSuccess) return rc;
@@ -307,31 +352,16 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
     }
   }
   const void* fn = tma_ok ? kv->kernel_tma : kv->kernel_plain;
-  SODA_CHECK(cudaFuncSetAttribute(fn,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  kv->smem_bytes),
-             kDeviceRunFailed);
-  int per_sm = 0;
-  SODA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                 &per_sm, fn, kv->threads, kv->smem_bytes),
-             kDeviceRunFailed);
-  if (per_sm < 1) {
-    fprintf(stderr, "ERROR: kernel of %s does not fit on an SM (%d B smem)\n",
-            prog.app_name, kv->smem_bytes);
-    return kDeviceRunFailed;
-  }
-  const long long resident =
-      static_cast<long long>(per_sm) * g_device.sm_count;
   const int rows = row_end - row_begin;
-  // 2-D register kernels pack `tiles_per_block` independent strips in a block
-  const int per_block = std::max(1, kv->tiles_per_block);
-  const long long grid_x = (tile_blocks + per_block - 1) / per_block;
-  int chunks = pick_chunks(grid_x, resident, rows, kv->lead + kv->out_delay,
-                           std::max(1, kv->trip));
-  if (const char* forced = getenv("SODA_CUDA_CHUNKS"))
-    chunks = std::max(1, std::min(rows, atoi(forced)));
-  args.chunk_rows = (rows + chunks - 1) / chunks;
-  chunks = (rows + args.chunk_rows - 1) / args.chunk_rows;
+  long long grid_x = 0;
+  int per_sm = 0;
+  const int chosen = choose_chunk_rows(prog, kv, fn, dims, rows, &grid_x,
+                                       &per_sm);
+  if (chosen < 0) return chosen;
+  args.chunk_rows = forced_chunk_rows > 0 ? std::min(forced_chunk_rows, rows)
+                                          : chosen;
+  const int chunks = (rows + args.chunk_rows - 1) / args.chunk_rows;
+  if (chunks > 65535) return kBufferExtentsTooLarge;
 
   dim3 grid(static_cast<unsigned>(grid_x), static_cast<unsigned>(chunks));
   dim3 block(kv->threads);

@@ -102,7 +102,12 @@ int run_device(const ProgramDesc& prog, const void* const* inputs,
 int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
            void* const* outputs, const int32_t* dims, int row_begin,
            int row_end, const int32_t* valid_lo, const int32_t* valid_hi,
-           cudaStream_t stream);
+           cudaStream_t stream, int forced_chunk_rows = 0);
+
+// Rows per block along the streamed dimension that `launch` picks for a range
+// of `rows` rows (whole waves of resident blocks); negative = error code.
+int chunk_rows(const ProgramDesc& prog, int depth, const int32_t* dims,
+               int rows);
 
 // Stream-ordered flag in device memory (local or peer-mapped): written and
 // awaited by the GPU front end, not by a kernel.

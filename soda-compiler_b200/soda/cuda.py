@@ -174,6 +174,10 @@ class Library:
          [voidpp, voidpp, i32p, c_int, c_void_p]),
         ('soda_cuda_launch', c_int,
          [c_int, voidpp, voidpp, i32p, c_int, c_int, i32p, i32p, c_void_p]),
+        ('soda_cuda_launch_chunked', c_int,
+         [c_int, voidpp, voidpp, i32p, c_int, c_int, i32p, i32p, c_int,
+          c_void_p]),
+        ('soda_cuda_chunk_rows', c_int, [c_int, i32p, c_int]),
         ('soda_cuda_depths', c_int, [i32p, c_int]),
         ('soda_cuda_flag_write', c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
         ('soda_cuda_flag_wait_geq', c_int,
@@ -354,15 +358,25 @@ class Library:
       raise CudaError('soda_cuda_flag_wait_geq', code)
 
   def launch(self, depth, inputs, outputs, dims, row_begin, row_end,
-             valid_lo, valid_hi, stream=None):
-    """Enqueue one kernel launch (see soda_cuda_launch)."""
+             valid_lo, valid_hi, stream=None, chunk_rows=0):
+    """Enqueue one kernel launch (see soda_cuda_launch[_chunked])."""
     pad = lambda xs, fill: (ctypes.c_int32 * 4)(
         *(list(xs) + [fill] * (4 - len(xs))))
-    code = self._lib.soda_cuda_launch(
+    code = self._lib.soda_cuda_launch_chunked(
         depth, self._pointers(inputs), self._pointers(outputs), pad(dims, 1),
-        row_begin, row_end, pad(valid_lo, 0), pad(valid_hi, 1), stream)
+        row_begin, row_end, pad(valid_lo, 0), pad(valid_hi, 1),
+        chunk_rows or 0, stream)
     if code:
       raise CudaError('soda_cuda_launch(%s)' % self.app_name, code)
+
+  def chunk_rows(self, depth, dims, rows):
+    """Rows per block a launch over ``rows`` streamed rows would use."""
+    value = self._lib.soda_cuda_chunk_rows(
+        depth, (ctypes.c_int32 * 4)(*(list(dims) + [1] * (4 - len(dims)))),
+        rows)
+    if value <= 0:
+      raise CudaError('soda_cuda_chunk_rows(%s)' % self.app_name, value)
+    return value
 
 
 _loaded = {}

@@ -126,8 +126,12 @@ class SlabRunner:
     if self.on_gpu:
       self.main = torch.cuda.current_stream(self.device)
       self.comm = torch.cuda.Stream(self.device)
-      self.side = torch.cuda.Stream(self.device)
+      # the face launches: high priority, so their blocks are dispatched
+      # before those of the interior launch queued next to them
+      self.face_streams = [torch.cuda.Stream(self.device, priority=-1)
+                           for _ in range(2)]
     self.launch_count = 0
+    self._chunk_cache = {}
     if exchange == 'p2p':
       self._setup_p2p()
 
@@ -284,11 +288,41 @@ class SlabRunner:
 
   # ---- compute ----------------------------------------------------------
   def _launch(self, depth, inputs, outputs, local_dims, row_begin, row_end,
-              valid_lo, valid_hi):
+              valid_lo, valid_hi, chunk_rows=0):
     self.library.launch(depth, inputs, outputs, local_dims, row_begin,
                         row_end, valid_lo, valid_hi,
-                        torch.cuda.current_stream(self.device).cuda_stream)
+                        torch.cuda.current_stream(self.device).cuda_stream,
+                        chunk_rows)
     self.launch_count += 1
+
+  def _split(self, depth, a, b):
+    """``(low_face, high_face, chunk_rows)``: [a, low_face) and
+    [high_face, b) are computed first and sent to the neighbours.
+
+    On GPUs the faces are whole blocks of the decomposition the library picks
+    for the slab (``chunk_rows`` rows each): a block pays a lead-in of
+    ``lead + delay`` rows before its first result, so a face of just the
+    ``reach`` rows a neighbour needs would stream most of its rows twice
+    (heat3d on 4 GPUs: 2 x 8 plane-steps per launch for 2 x 2 planes, 6 % of
+    the slab).  Cut at block boundaries, the three launches together are
+    exactly the blocks of the one-launch decomposition."""
+    need_lo = self.reach_hi if self.rank > 0 else 0         # rows from a up
+    need_hi = self.reach_lo if self.rank + 1 < self.world else 0
+    chunk = 0
+    if self.on_gpu and self._compute == self._launch:
+      key = (depth, b - a)
+      if key not in self._chunk_cache:
+        self._chunk_cache[key] = self.library.chunk_rows(
+            depth, self.local_dims, b - a)
+      chunk = self._chunk_cache[key]
+      round_up = lambda n: -(-n // chunk) * chunk
+      if round_up(need_lo) + round_up(need_hi) < b - a:
+        need_lo, need_hi = round_up(need_lo), round_up(need_hi)
+      else:
+        chunk = 0       # thin slab: minimal faces, chunks chosen per launch
+    low_face = min(b, a + need_lo)
+    high_face = max(low_face, b - need_hi)
+    return low_face, high_face, chunk
 
   def plan(self, iterate):
     """Depths of the launches that make up ``iterate`` iterations."""
@@ -350,45 +384,52 @@ class SlabRunner:
       if p2p and n:
         self._await_ghosts()
 
-      def go(row_begin, row_end, current=current, target=target, lo=lo,
-             hi=hi, depth=depth):
+      def go(row_begin, row_end, chunk=0, current=current, target=target,
+             lo=lo, hi=hi, depth=depth):
         if row_end > row_begin:
-          self._compute(depth, current, target, self.local_dims, row_begin,
-                        row_end, lo, hi)
+          if chunk:
+            self._compute(depth, current, target, self.local_dims, row_begin,
+                          row_end, lo, hi, chunk)
+          else:
+            self._compute(depth, current, target, self.local_dims, row_begin,
+                          row_end, lo, hi)
       if last or self.world == 1:
         go(a, b)
       else:
         # faces first, so their transfer overlaps the interior
-        low_face = min(b, a + self.reach_hi) if self.rank > 0 else a
-        high_face = max(low_face, b - self.reach_lo) \
-            if self.rank + 1 < self.world else b
-        if self.on_gpu and low_face > a and b > high_face:
-          # two faces (a rank with two neighbours): small launches, run them
-          # side by side instead of one after the other
+        low_face, high_face, chunk = self._split(depth, a, b)
+        faces = [(a, low_face), (high_face, b)]
+        face_events = []
+        if self.on_gpu:
+          # each face on its own high-priority stream, the interior next to
+          # them on the main stream: the faces' blocks go first, the interior
+          # fills the SMs as they drain
           begun = self.main.record_event()
-          with torch.cuda.stream(self.side):
-            self.side.wait_event(begun)
-            go(high_face, b)
-            high_done = self.side.record_event()
-          go(a, low_face)
-          self.main.wait_event(high_done)
+          for stream, (r0, r1) in zip(self.face_streams, faces):
+            if r1 > r0:
+              with torch.cuda.stream(stream):
+                stream.wait_event(begun)
+                go(r0, r1, chunk)
+                face_events.append(stream.record_event())
         else:
-          go(a, low_face)
-          go(high_face, b)
+          for r0, r1 in faces:
+            go(r0, r1)
         fed = [target[out] for out in self.feedback.values()]
         if p2p:
-          faces_done = self.main.record_event()
           with torch.cuda.stream(self.comm):
-            self.comm.wait_event(faces_done)
+            for event in face_events:
+              self.comm.wait_event(event)
             self._push_faces(target, n % len(self.buffers), n == 0)
         elif self.on_gpu:
-          faces_done = self.main.record_event()
           with torch.cuda.stream(self.comm):
-            self.comm.wait_event(faces_done)
+            for event in face_events:
+              self.comm.wait_event(event)
             pending = self._exchange(fed)
         else:
           pending = self._exchange(fed)
-        go(low_face, high_face)
+        go(low_face, high_face, chunk)
+        for event in face_events:      # the next launch reads the faces too
+          self.main.wait_event(event)
       if not last:
         nxt = list(current)
         for inp, out in self.feedback.items():

@@ -60,9 +60,15 @@ def bits(array):
                      8: np.uint64}[array.dtype.itemsize])
 
 
-def assert_bit_exact(got, want, what=''):
+def assert_bit_exact(got, want, what='', any_nan=False):
+  """``any_nan``: a NaN matches a NaN of any sign/payload.  The default NaN
+  an invalid operation produces is a property of the machine (x86 SSE:
+  0xFFC00000, NVIDIA: 0x7FFFFFFF), not of the program; everything else, the
+  infinities included, still compares bit for bit."""
   assert got.shape == want.shape and got.dtype == want.dtype, what
   same = bits(got) == bits(want)
+  if any_nan and got.dtype.kind == 'f':
+    same |= np.isnan(got) & np.isnan(want)
   if not same.all():
     bad = np.argwhere(~same)
     first = tuple(bad[0])
