@@ -309,7 +309,8 @@ class SlabRunner:
     need_lo = self.reach_hi if self.rank > 0 else 0         # rows from a up
     need_hi = self.reach_lo if self.rank + 1 < self.world else 0
     chunk = 0
-    if self.on_gpu and self._compute == self._launch:
+    if (self.on_gpu and self._compute == self._launch and
+        os.environ.get('SODA_CUDA_SLAB_FACES', 'chunk') != 'minimal'):
       key = (depth, b - a)
       if key not in self._chunk_cache:
         self._chunk_cache[key] = self.library.chunk_rows(
