@@ -124,6 +124,10 @@ int soda_cuda_launch_chunked(int depth, const void* const* inputs,
 /* Rows per block soda_cuda_launch picks for `rows` streamed rows of a grid of
  * extents `dims` (whole waves of resident blocks on this device); < 0: error. */
 int soda_cuda_chunk_rows(int depth, const int32_t* dims, int rows);
+/* Streamed rows a block of the depth-`depth` kernel runs through besides the
+ * rows it owns (lead-in + drain): the price of one more launch over a row
+ * range.  < 0: error. */
+int soda_cuda_lead_rows(int depth);
 /* Fills up to `max` compiled depths (decreasing); returns how many exist. */
 int soda_cuda_depths(int32_t* depths, int max);
 

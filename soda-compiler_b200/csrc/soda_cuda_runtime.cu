@@ -269,6 +269,13 @@ int chunk_rows(const ProgramDesc& prog, int depth, const int32_t* dims,
                            nullptr);
 }
 
+int lead_rows(const ProgramDesc& prog, int depth) {
+  const KernelVariant* kv = find_variant(prog, depth);
+  if (kv == nullptr) return kInternalError;
+  const int trip = std::max(1, kv->trip);
+  return (kv->lead + kv->out_delay + trip - 1) / trip * trip;
+}
+
 int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
            void* const* outputs, const int32_t* dims, int row_begin,
            int row_end, const int32_t* valid_lo, const int32_t* valid_hi,

@@ -109,6 +109,10 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
 int chunk_rows(const ProgramDesc& prog, int depth, const int32_t* dims,
                int rows);
 
+// Streamed rows a block runs through before and after the rows it owns (its
+// lead-in and drain): what every extra launch over a row range costs.
+int lead_rows(const ProgramDesc& prog, int depth);
+
 // Stream-ordered flag in device memory (local or peer-mapped): written and
 // awaited by the GPU front end, not by a kernel.
 int flag_write(void* flag, uint32_t value, cudaStream_t stream);

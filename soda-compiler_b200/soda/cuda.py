@@ -178,6 +178,7 @@ class Library:
          [c_int, voidpp, voidpp, i32p, c_int, c_int, i32p, i32p, c_int,
           c_void_p]),
         ('soda_cuda_chunk_rows', c_int, [c_int, i32p, c_int]),
+        ('soda_cuda_lead_rows', c_int, [c_int]),
         ('soda_cuda_depths', c_int, [i32p, c_int]),
         ('soda_cuda_flag_write', c_int, [c_void_p, ctypes.c_uint32, c_void_p]),
         ('soda_cuda_flag_wait_geq', c_int,
@@ -368,6 +369,13 @@ class Library:
         chunk_rows or 0, stream)
     if code:
       raise CudaError('soda_cuda_launch(%s)' % self.app_name, code)
+
+  def lead_rows(self, depth):
+    """Rows a block streams besides the rows it owns (lead-in + drain)."""
+    value = self._lib.soda_cuda_lead_rows(depth)
+    if value < 0:
+      raise CudaError('soda_cuda_lead_rows(%s)' % self.app_name, value)
+    return value
 
   def chunk_rows(self, depth, dims, rows):
     """Rows per block a launch over ``rows`` streamed rows would use."""

@@ -299,23 +299,31 @@ class SlabRunner:
     """``(low_face, high_face, chunk_rows)``: [a, low_face) and
     [high_face, b) are computed first and sent to the neighbours.
 
-    On GPUs the faces are whole blocks of the decomposition the library picks
-    for the slab (``chunk_rows`` rows each): a block pays a lead-in of
-    ``lead + delay`` rows before its first result, so a face of just the
-    ``reach`` rows a neighbour needs would stream most of its rows twice
-    (heat3d on 4 GPUs: 2 x 8 plane-steps per launch for 2 x 2 planes, 6 % of
-    the slab).  Cut at block boundaries, the three launches together are
-    exactly the blocks of the one-launch decomposition."""
+    A block pays a lead-in of ``lead_rows`` rows besides the rows it owns, so
+    a face of just the ``reach`` rows a neighbour needs streams most of its
+    rows twice.  Where that is a visible share of the slab (3-D programs:
+    heat3d on 4 GPUs, 2 x 6 extra plane-steps per launch on 256 planes) the
+    faces are instead whole blocks of the decomposition the library picks for
+    the slab (``chunk_rows`` rows each): cut at block boundaries, the three
+    launches together are exactly the blocks of the one-launch decomposition.
+    Where it is not (2-D programs: 25 extra rows on 16384), minimal faces
+    measured 2 % faster (profiles/README.md, capture r1p).
+    SODA_CUDA_SLAB_FACES=minimal|chunk overrides the choice."""
     need_lo = self.reach_hi if self.rank > 0 else 0         # rows from a up
     need_hi = self.reach_lo if self.rank + 1 < self.world else 0
     chunk = 0
-    if (self.on_gpu and self._compute == self._launch and
-        os.environ.get('SODA_CUDA_SLAB_FACES', 'chunk') != 'minimal'):
+    if self.on_gpu and self._compute == self._launch:
+      mode = os.environ.get('SODA_CUDA_SLAB_FACES')
+      if mode not in ('minimal', 'chunk'):
+        faces = (1 if need_lo else 0) + (1 if need_hi else 0)
+        extra = faces * self.library.lead_rows(depth)
+        mode = 'chunk' if extra > 0.01 * (b - a) else 'minimal'
       key = (depth, b - a)
-      if key not in self._chunk_cache:
+      if mode == 'chunk' and key not in self._chunk_cache:
         self._chunk_cache[key] = self.library.chunk_rows(
             depth, self.local_dims, b - a)
-      chunk = self._chunk_cache[key]
+      chunk = self._chunk_cache[key] if mode == 'chunk' else 0
+    if chunk:
       round_up = lambda n: -(-n // chunk) * chunk
       if round_up(need_lo) + round_up(need_hi) < b - a:
         need_lo, need_hi = round_up(need_lo), round_up(need_hi)

@@ -20,9 +20,12 @@ from soda.codegen import cuda as codegen          # noqa: E402
 
 def build(job):
   name, iterate, options = job
+  options = dict(options)
+  fast = bool(options.pop('fast', 0))
   stencil = core.Stencil.from_file(
       os.path.join(ROOT, 'benchmarks', name + '.soda'), iterate=iterate)
-  return soda_cuda.build(stencil, options=codegen.Options(**options))
+  return soda_cuda.build(stencil, fast_math=fast,
+                         options=codegen.Options(**options))
 
 
 def main():

@@ -64,10 +64,11 @@ def main():
   for text in sys.argv[1:]:
     name, iterate, dims, options = parse_case(text)
     e2e = options.pop('e2e', 0)
+    fast = bool(options.pop('fast', 0))   # -DSODA_CUDA_FAST_MATH build
     with open(os.path.join(ROOT, 'benchmarks', name + '.soda')) as handle:
       stencil = core.Stencil.from_text(handle.read(), iterate=iterate)
     try:
-      library = soda_cuda.compile_stencil(stencil,
+      library = soda_cuda.compile_stencil(stencil, fast_math=fast,
                                           options=codegen.Options(**options))
     except Exception as e:   # pylint: disable=broad-except
       print('%-50s build failed: %s' % (text, str(e)[:300]))
