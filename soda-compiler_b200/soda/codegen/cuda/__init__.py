@@ -27,6 +27,7 @@ from soda.codegen.cuda import host as host_mod
 from soda.codegen.cuda import kernel as kernel_mod
 from soda.codegen.cuda import kernel_reg as kernel_reg_mod
 from soda.codegen.cuda import plan as plan_mod
+from soda.codegen.cuda import tuned as tuned_mod
 
 SUPPORTED_TYPES = {
     'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32', 'int64',
@@ -75,6 +76,13 @@ def add_arguments(parser):
       help='evaluate fused iterations k and k + depth/2 together on packed '
       'f32x2 arithmetic (default: whenever the program allows it)')
   parser.add_argument(
+      '--cuda-autotune', type=int, nargs='+', dest='cuda_autotune',
+      metavar='N',
+      help='grid extents to tune the kernel configuration for, on the GPU of '
+      'this machine (times the candidates of soda.cuda_tune and records the '
+      'winner in tuned.json before emitting); the GPU counterpart of '
+      'exploring --tile-size / --unroll-factor')
+  parser.add_argument(
       '--cuda-style', type=str, dest='cuda_style', choices=['reg', 'ring'],
       help='kernel family: `reg` keeps the streamed window of every tensor '
       'in registers and shares dimension-0 neighbours by warp shuffle '
@@ -104,6 +112,9 @@ class Options:
                paired=getattr(args, 'cuda_paired', None),
                min_blocks=getattr(args, 'cuda_min_blocks', None),
                groups=getattr(args, 'cuda_groups', None))
+
+  def is_default(self):
+    return all(v is None for v in vars(self).values())
 
   def key(self):
     return 'd%s_t%s_n%s_v%s_p%s_%s_%s_%s_g%s' % (
@@ -289,6 +300,10 @@ def make_schedules(program, options=None):
   not divide ``iterate``, the depth of the remainder."""
   options = options or Options()
   check_supported(program)
+  if options.is_default():
+    found = tuned_mod.lookup(program)     # soda.cuda_tune's winner, if any
+    if found:
+      options = Options(**found)
   iterate = program.iterate
   if options.depth:
     main = max(1, min(options.depth, iterate))
@@ -374,6 +389,15 @@ def print_code(stencil, args):
     return
   program = plan_mod.extract_program(stencil)
   check_supported(program)
+  dims = getattr(args, 'cuda_autotune', None)
+  if dims:
+    if len(dims) != program.dim:
+      raise util.SemanticError('--cuda-autotune takes %d extents' %
+                               program.dim)
+    from soda import cuda_tune     # needs nvcc and a GPU
+    results = cuda_tune.tune(stencil, tuple(dims))
+    if results and results[0][1]:
+      cuda_tune.record(program, dims, results[0][0], results[0][1])
   if kernel_file is not None:
     schedules = make_schedules(program, Options.from_args(args))
     _emit(kernel_file, lambda f: print_kernel(program, schedules, f))

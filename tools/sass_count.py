@@ -37,11 +37,17 @@ def loop_stats(sass):
   insts = [(int(m.group(1), 16), m.group(2), m.group(4))
            for m in map(LINE.search, sass.splitlines()) if m]
   best = None
+  exits = [addr for addr, op, _ in insts if op == 'EXIT']
   for addr, op, rest in insts:
     if op == 'BRA':
       target = re.search(r'0x([0-9a-f]+)', rest)
       if target and int(target.group(1), 16) < addr:
         span = (int(target.group(1), 16), addr)
+        # ptxas parks cold blocks (the unconverged-warp form of every
+        # shuffle) after the kernel's EXIT and branches back from there:
+        # those are not loops
+        if any(span[0] <= e <= span[1] for e in exits):
+          continue
         if best is None or span[1] - span[0] > best[1] - best[0]:
           best = span
   if best is None:
