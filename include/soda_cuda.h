@@ -96,6 +96,23 @@ int soda_cuda_window(int iterate, int32_t lo[4], int32_t hi[4]);
 int soda_cuda_run(buffer_t* const* inputs, buffer_t* const* outputs,
                   const char* config);
 
+/* `param` statements (small constant arrays; reference grammar.py:38, passed
+ * after the outputs by the reference entry, header.py:57-60).  A param is a
+ * C array `T name[s0][s1]..` (first index slowest, reference
+ * host.py:1004-1008) in host memory.  soda_cuda_run_params is soda_cuda_run
+ * with the param buffers (extent[d] = size[d], elem_size checked);
+ * soda_cuda_set_params uploads raw host arrays for callers of the
+ * device-level entry points — the values stay in effect until set again.
+ * Programs with params refuse to launch (-12) before they are set. */
+int soda_cuda_num_params(void);
+const char* soda_cuda_param_name(int index);
+const char* soda_cuda_param_type(int index);
+/* Fills size[0..rank) and returns the rank; < 0: no such param. */
+int soda_cuda_param_size(int index, int32_t size[4]);
+int soda_cuda_run_params(buffer_t* const* inputs, buffer_t* const* outputs,
+                         buffer_t* const* params, const char* config);
+int soda_cuda_set_params(const void* const* host_arrays);
+
 /* Device-resident dense arrays, `iterate` iterations (0: the program's own),
  * enqueued on `stream` (a cudaStream_t; NULL = default stream), asynchronous.
  * Inputs are not modified. */

@@ -46,6 +46,7 @@ struct Device {
 std::mutex g_mutex;
 Device g_device;
 soda_cuda_stats_t g_stats;
+void* g_param_dev[kRtMaxTensors] = {};   // device copies of the param arrays
 cudaEvent_t g_ev[6];   // kernel start/stop, h2d start/stop, d2h start/stop
 bool g_ev_ready = false;
 bool g_stats_pending = false;
@@ -269,6 +270,27 @@ int chunk_rows(const ProgramDesc& prog, int depth, const int32_t* dims,
                            nullptr);
 }
 
+int set_params(const ProgramDesc& prog, const void* const* host_arrays) {
+  std::lock_guard<std::mutex> lock(g_mutex);
+  int rc = ensure_device();
+  if (rc != kSuccess) return rc;
+  for (int k = 0; k < prog.n_param; ++k) {
+    if (host_arrays == nullptr || host_arrays[k] == nullptr)
+      return kBufferArgumentIsNull;
+    size_t bytes = static_cast<size_t>(prog.param_elem[k]);
+    for (int d = 0; d < prog.param_rank[k]; ++d) bytes *= prog.param_size[k][d];
+    if (g_param_dev[k] == nullptr)
+      SODA_CHECK(cudaMalloc(&g_param_dev[k], std::max<size_t>(bytes, 16)),
+                 kDeviceMallocFailed);
+    // earlier launches may still be reading the previous values
+    SODA_CHECK(cudaDeviceSynchronize(), kDeviceSyncFailed);
+    SODA_CHECK(cudaMemcpy(g_param_dev[k], host_arrays[k], bytes,
+                          cudaMemcpyHostToDevice),
+               kCopyToDeviceFailed);
+  }
+  return kSuccess;
+}
+
 int lead_rows(const ProgramDesc& prog, int depth) {
   const KernelVariant* kv = find_variant(prog, depth);
   if (kv == nullptr) return kInternalError;
@@ -328,6 +350,15 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
     if (reinterpret_cast<uintptr_t>(outputs[k]) % 16 != 0) aligned = false;
   }
   args.vec_store = aligned ? 1 : 0;
+  for (int k = 0; k < prog.n_param; ++k) {
+    if (g_param_dev[k] == nullptr) {
+      fprintf(stderr, "ERROR: param %s of %s has not been set "
+                      "(soda_cuda_set_params)\n",
+              prog.param_name[k], prog.app_name);
+      return kBufferArgumentIsNull;
+    }
+    args.param_ptr[k] = g_param_dev[k];
+  }
 
   if (tma_ok && kv->uses_tma) {
     for (int k = 0; k < prog.n_in; ++k) {
@@ -647,7 +678,8 @@ int run_pipelined(const ProgramDesc& prog, buffer_t* const* inputs,
 }  // namespace
 
 int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
-                buffer_t* const* outputs, const char* config) {
+                buffer_t* const* outputs, const char* config,
+                buffer_t* const* params) {
   (void)config;
   for (int k = 0; k < prog.n_in; ++k)
     if (inputs == nullptr || inputs[k] == nullptr) return kBufferArgumentIsNull;
@@ -690,6 +722,27 @@ int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
               prog.in_elem[k]);
       return kBadElemSize;
     }
+
+  if (prog.n_param > 0 && params != nullptr) {
+    // param arrays: small, host memory, uploaded before the launches
+    const void* host_arrays[kRtMaxTensors] = {};
+    for (int k = 0; k < prog.n_param; ++k) {
+      const buffer_t* b = params[k];
+      if (b == nullptr || b->host == nullptr) return kBufferArgumentIsNull;
+      if (b->elem_size != prog.param_elem[k]) {
+        fprintf(stderr, "ERROR: Buffer %s has type %s but elem_size of the "
+                        "buffer passed in is %d instead of %d\n",
+                prog.param_name[k], prog.param_type[k], b->elem_size,
+                prog.param_elem[k]);
+        return kBadElemSize;
+      }
+      for (int d = 0; d < prog.param_rank[k]; ++d)
+        if (b->extent[d] != prog.param_size[k][d]) return kAccessOutOfBounds;
+      host_arrays[k] = b->host;
+    }
+    const int rc_params = set_params(prog, host_arrays);
+    if (rc_params != kSuccess) return rc_params;
+  }
 
   int32_t dims[kRtMaxDim] = {1, 1, 1, 1};
   long long cells = 1;
@@ -895,6 +948,10 @@ void release_all() {
   for (auto& e : g_pool)
     if (e.ptr != nullptr) cudaFree(e.ptr);
   g_pool.clear();
+  for (void*& p : g_param_dev) {
+    if (p != nullptr) cudaFree(p);
+    p = nullptr;
+  }
 }
 
 }  // namespace soda

@@ -64,6 +64,15 @@ struct ProgramDesc {
   int stencil_dim[kRtMaxDim];
   int n_variants;
   const KernelVariant* variants;         // sorted by decreasing depth
+  // `param` statements: small constant arrays passed after the outputs
+  // (reference header.py:57-60); C arrays `T name[s0][s1]..`, first index
+  // slowest (host.py:1004-1008).
+  int n_param;
+  const char* param_name[kRtMaxTensors];
+  const char* param_type[kRtMaxTensors];
+  int param_elem[kRtMaxTensors];         // bytes per element
+  int param_rank[kRtMaxTensors];
+  int param_size[kRtMaxTensors][kRtMaxDim];
 };
 
 // Result codes: the Halide error numbering the reference host uses
@@ -87,7 +96,13 @@ enum {
 
 // `<app>(buffer_t*..., const char*)`: host or device buffers, bounds query.
 int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
-                buffer_t* const* outputs, const char* config);
+                buffer_t* const* outputs, const char* config,
+                buffer_t* const* params = nullptr);
+
+// Copies the program's param arrays (host memory, one pointer per param, in
+// program order) to the device; every later launch of this library reads
+// them.  `run_buffers` calls this when it is given params.
+int set_params(const ProgramDesc& prog, const void* const* host_arrays);
 
 // All `iterate` iterations on device-resident dense arrays, asynchronously on
 // `stream`.  Inputs are not modified.

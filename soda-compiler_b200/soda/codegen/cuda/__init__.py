@@ -129,9 +129,9 @@ def check_supported(program):
       raise util.SemanticError(
           'type `%s` of `%s` is not supported by the CUDA backend' %
           (haoda_type, name))
-  if program.params:
-    raise util.SemanticError('param statements are not supported by the CUDA '
-                             'backend yet')
+  if len(program.params) > 8:
+    raise util.SemanticError('at most 8 params')
+  program.check_params()
   if not 2 <= program.dim <= 4:
     raise util.SemanticError('the CUDA backend handles 2- to 4-dimensional '
                              'programs, not %d' % program.dim)
@@ -357,7 +357,8 @@ def print_header(program, header_file):
   reduced to the buffer_t definition and the prototype."""
   p = util.Printer(header_file)
   guard = 'HALIDE_%s_H_' % program.app_name.upper()
-  names = [n for n, _ in program.inputs] + [n for n, _ in program.outputs]
+  names = ([n for n, _ in program.inputs] + [n for n, _ in program.outputs] +
+           list(program.params))       # reference header.py:57
   p.printlns('#ifndef %s' % guard, '#define %s' % guard, '',
              '#include "soda_cuda.h"  // buffer_t', '',
              '#ifndef HALIDE_FUNCTION_ATTRS', '#define HALIDE_FUNCTION_ATTRS',

@@ -127,6 +127,7 @@ def emit_kernel(p, sched):
   p.println('uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw + %d);'
             % lay.bar_offset)
   p.println('const int tid = threadIdx.x;')
+  plan_mod.emit_param_pointers(p, sched.program)
   p.println()
   p.println('// this block: one tile of the non-streamed dims, one chunk of '
             'the streamed dim')
@@ -348,6 +349,8 @@ def _emit_stage(p, sched, lay, node):
       node.loads))
 
   def ref_code(load):
+    if load.parent in sched.program.params:
+      return plan_mod.param_code(sched.program, load)
     parent, off = resolved[load]
     g, xlo = window_of[(parent.index, off[1:])]
     return 'w%d[k + %d]' % (g, off[0] - xlo)

@@ -227,6 +227,7 @@ class _Emitter:
     p.println('const int tid = threadIdx.x;')
     p.println('const int lane = tid & 31;')
     p.println('(void)lane;')
+    plan_mod.emit_param_pointers(p, sched.program)
     p.println()
     self.emit_geometry()
     self.emit_histories()
@@ -723,6 +724,8 @@ class _Emitter:
         node.loads))
 
     def ref_code(load, k):
+      if load.parent in sched.program.params:
+        return plan_mod.param_code(sched.program, load)
       parent, off = resolved[load]
       if sched.via_smem(off):
         g, xlo = window_of[(parent.index, off[1:])]

@@ -58,7 +58,9 @@ class Code:
 class Stage:
   """One local/output statement of one iteration."""
 
-  def __init__(self, name, haoda_type, lets, expr, store_idx, is_output):
+  def __init__(self, name, haoda_type, lets, expr, store_idx, is_output,
+               params=()):
+    self.params = frozenset(params)   # names of param arrays
     self.name = name
     self.haoda_type = haoda_type
     self.c_type = util.get_c_type(haoda_type)
@@ -71,6 +73,10 @@ class Stage:
       node.visit(self._note_load)
 
   def load_of(self, ref):
+    if ref.name in self.params:
+      # a param is a small constant array indexed absolutely (the golden
+      # loop reads `<name>_img[i][j]`, reference host.py:1095-1097)
+      return Load(ref.name, tuple(ref.idx))
     return Load(ref.name,
                 tuple(a - b for a, b in zip(ref.idx, self.store_idx)))
 
@@ -110,6 +116,10 @@ class Program:
 
   def __init__(self, app_name, dim, iterate, inputs, outputs, stages,
                params=()):
+    # params: [(name, haoda_type, size tuple)] — small constant arrays passed
+    # next to the tensors (reference header.py:57-60)
+    self.param_stmts = [(n, t, tuple(size)) for n, t, size in params]
+    params = [n for n, _, _ in self.param_stmts]
     self.app_name = app_name
     self.dim = dim
     self.iterate = iterate
@@ -121,12 +131,38 @@ class Program:
     self.output_names = [n for n, _ in self.outputs]
     self.types = dict(self.inputs)
     self.types.update((s.name, s.haoda_type) for s in self.stages)
+    self.types.update((n, t) for n, t, _ in self.param_stmts)
     # output k of an iteration is input k of the next (by position)
     self.feedback = (dict(zip(self.input_names, self.output_names))
                      if len(self.inputs) == len(self.outputs) else {})
 
   def c_type(self, name):
     return util.get_c_type(self.types[name])
+
+  def param_index(self, name):
+    return self.params.index(name)
+
+  def param_flat(self, load):
+    """Flat element index of a param load: the golden loop declares
+    ``T <name>_img[s0][s1]..`` and reads ``<name>_img[i][j]..`` (reference
+    host.py:1004-1008, 1095-1097), i.e. the first index is the slowest."""
+    size = self.param_stmts[self.param_index(load.parent)][2]
+    if len(load.off) != len(size):
+      raise util.SemanticError('param `%s` has %d dimension(s), indexed with '
+                               '%d' % (load.parent, len(size), len(load.off)))
+    flat = 0
+    for index, extent in zip(load.off, size):
+      if not 0 <= index < extent:
+        raise util.SemanticError('index %s is outside param `%s`%s' % (
+            tuple(load.off), load.parent, list(size)))
+      flat = flat * extent + index
+    return flat
+
+  def check_params(self):
+    for stage in self.stages:
+      for load in stage.loads:
+        if load.parent in self.params:
+          self.param_flat(load)
 
   def elem_size(self, name):
     return util.get_width_in_bytes(self.types[name])
@@ -193,6 +229,22 @@ class Program:
     return [(max(0, -l), d - max(0, h)) for l, h, d in zip(lo, hi, dims)]
 
 
+def emit_param_pointers(p, program):
+  """Kernel prologue: one typed pointer per param array (device copies made
+  by the runtime, passed in StreamArgs::param_ptr)."""
+  for k, (name, haoda_type, _) in enumerate(program.param_stmts):
+    c_type = util.get_c_type(haoda_type)
+    p.println('const %s* const prm_%s = static_cast<const %s*>('
+              'a.param_ptr[%d]);' % (c_type, name, c_type, k))
+    p.println('(void)prm_%s;' % name)
+
+
+def param_code(program, load):
+  """Device code of a param load: a uniform read-only load the compiler
+  hoists out of the streamed loop."""
+  return '__ldg(prm_%s + %d)' % (load.parent, program.param_flat(load))
+
+
 def extract_program(stencil):
   """soda.core.Stencil (ours or, duck-typed, the reference's) -> Program."""
   n_in = len(stencil.input_stmts)
@@ -204,7 +256,8 @@ def extract_program(stencil):
   replicas = list(stencil.tensors.values())[n_in:n_in + len(stage_names)]
   by_name = {
       name: Stage(name, tensor.haoda_type, tensor.lets, tensor.expr,
-                  tensor.st_ref.idx, name in output_names)
+                  tensor.st_ref.idx, name in output_names,
+                  params=stencil.param_names)
       for name, tensor in zip(stage_names, replicas)}
   known = set(stencil.input_names) | set(stencil.param_names)
   placed, order, pending = set(known), [], list(stage_names)
@@ -225,7 +278,8 @@ def extract_program(stencil):
       stencil.app_name, stencil.dim, stencil.iterate,
       list(zip(stencil.input_names, stencil.input_types)),
       list(zip(stencil.output_names, stencil.output_types)),
-      order, params=list(stencil.param_names))
+      order, params=[(stmt.name, stmt.haoda_type, tuple(stmt.size))
+                     for stmt in stencil.param_stmts])
 
 
 # --- the fused, streamed schedule --------------------------------------------

@@ -170,6 +170,12 @@ class Library:
         ('soda_cuda_tensor_elem_size', c_int, [c_int, c_int]),
         ('soda_cuda_window', c_int, [c_int, i32p, i32p]),
         ('soda_cuda_run', c_int, [bufpp, bufpp, c_char_p]),
+        ('soda_cuda_run_params', c_int, [bufpp, bufpp, bufpp, c_char_p]),
+        ('soda_cuda_num_params', c_int, []),
+        ('soda_cuda_param_name', c_char_p, [c_int]),
+        ('soda_cuda_param_type', c_char_p, [c_int]),
+        ('soda_cuda_param_size', c_int, [c_int, i32p]),
+        ('soda_cuda_set_params', c_int, [voidpp]),
         ('soda_cuda_run_device', c_int,
          [voidpp, voidpp, i32p, c_int, c_void_p]),
         ('soda_cuda_launch', c_int,
@@ -205,6 +211,13 @@ class Library:
                     for k in range(lib.soda_cuda_num_outputs())]
     depths = (ctypes.c_int32 * 16)()
     self.depths = list(depths[:lib.soda_cuda_depths(depths, 16)])
+    self.params = []            # [(name, haoda type, size tuple)]
+    for k in range(lib.soda_cuda_num_params()):
+      size = (ctypes.c_int32 * 4)()
+      rank = lib.soda_cuda_param_size(k, size)
+      self.params.append((lib.soda_cuda_param_name(k).decode(),
+                          lib.soda_cuda_param_type(k).decode(),
+                          tuple(size[:rank])))
 
   def window(self, iterate=None):
     """``(lo, hi)`` offsets per dim read by an output cell after ``iterate``."""
@@ -261,11 +274,41 @@ class Library:
     buf.elem_size = elem
     return buf, dims
 
-  def run(self, inputs, outputs=None):
+  def _param_arrays(self, params):
+    """The param arrays as C-contiguous numpy arrays of the declared type
+    and shape (``T name[s0][s1]``: numpy shape ``(s0, s1)``)."""
+    if isinstance(params, dict):
+      params = [params[name] for name, _, _ in self.params]
+    if params is None or len(params) != len(self.params):
+      raise ValueError('%s takes %d param array(s): %s' % (
+          self.app_name, len(self.params),
+          ', '.join(name for name, _, _ in self.params)))
+    arrays = []
+    for array, (name, haoda_type, size) in zip(params, self.params):
+      array = np.ascontiguousarray(array, dtype=NUMPY_TYPES[haoda_type])
+      if array.shape != size:
+        raise ValueError('param `%s` must have shape %s, got %s' % (
+            name, size, array.shape))
+      arrays.append(array)
+    return arrays
+
+  def set_params(self, params):
+    """Upload the param arrays for the device-level entry points
+    (run_device, launch); they stay in effect until set again."""
+    arrays = self._param_arrays(params)
+    pointers = (ctypes.c_void_p * len(arrays))(
+        *[a.ctypes.data for a in arrays])
+    code = self._lib.soda_cuda_set_params(pointers)
+    if code:
+      raise CudaError('soda_cuda_set_params(%s)' % self.app_name, code)
+
+  def run(self, inputs, outputs=None, params=None):
     """Run the whole program (all ``iterate`` iterations); returns outputs.
 
     ``inputs`` in program order.  ``outputs``: arrays to fill, or None to
     allocate them like the first input (numpy -> numpy, torch -> torch).
+    ``params``: the program's param arrays (list in program order or dict by
+    name), required if it declares any.
     """
     if len(inputs) != len(self.inputs):
       raise ValueError('%s takes %d input(s)' % (self.app_name,
@@ -293,7 +336,25 @@ class Library:
         *[ctypes.pointer(b) for b in in_bufs])
     out_ptrs = (ctypes.POINTER(BufferT) * len(out_bufs))(
         *[ctypes.pointer(b) for b in out_bufs])
-    code = self._lib.soda_cuda_run(in_ptrs, out_ptrs, None)
+    if self.params:
+      arrays = self._param_arrays(params)
+      param_bufs = []
+      for array, (_, haoda_type, size) in zip(arrays, self.params):
+        buf = BufferT()
+        buf.host = array.ctypes.data
+        buf.elem_size = util.get_width_in_bytes(haoda_type)
+        stride = 1
+        for d, extent in enumerate(size):
+          # the reference harness' descriptor of a param (host.py:1022-1030)
+          buf.extent[d], buf.stride[d] = extent, stride
+          stride *= extent
+        param_bufs.append(buf)
+      param_ptrs = (ctypes.POINTER(BufferT) * len(param_bufs))(
+          *[ctypes.pointer(b) for b in param_bufs])
+      code = self._lib.soda_cuda_run_params(in_ptrs, out_ptrs, param_ptrs,
+                                            None)
+    else:
+      code = self._lib.soda_cuda_run(in_ptrs, out_ptrs, None)
     if code:
       raise CudaError('soda_cuda_run(%s)' % self.app_name, code)
     return list(outputs)
@@ -402,15 +463,18 @@ def compile_stencil(stencil, **kwargs):
   return load(build(stencil, **kwargs))
 
 
-def run(stencil, arrays, **kwargs):
+def run(stencil, arrays, params=None, **kwargs):
   """Run ``stencil`` on ``arrays`` on the current CUDA device.
 
-  ``arrays``: the inputs in program order, or a dict by input name.  Returns
-  the outputs in program order (a dict by name if ``arrays`` was a dict).
+  ``arrays``: the inputs in program order, or a dict by input name (which may
+  also hold the param arrays by name).  Returns the outputs in program order
+  (a dict by name if ``arrays`` was a dict).
   """
   library = compile_stencil(stencil, **kwargs)
   if isinstance(arrays, dict):
     inputs = [arrays[name] for name, _ in library.inputs]
-    outputs = library.run(inputs)
+    if params is None and library.params:
+      params = [arrays[name] for name, _, _ in library.params]
+    outputs = library.run(inputs, params=params)
     return {name: out for (name, _), out in zip(library.outputs, outputs)}
-  return library.run(list(arrays))
+  return library.run(list(arrays), params=params)

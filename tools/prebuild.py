@@ -64,6 +64,11 @@ def main():
       print('%-40s %s' % ((name, options), os.path.relpath(soda_cuda.build(
           test_types_gpu.stencil_of(name),
           options=codegen.Options(**options)), ROOT)))
+    import param_programs
+    for name, _, options in param_programs.CASES:
+      print('%-40s %s' % ((name, options), os.path.relpath(soda_cuda.build(
+          param_programs.stencil_of(name),
+          options=codegen.Options(**options)), ROOT)))
     jobs += [(n, None, {}) for n in entry.BENCHMARKS]
     jobs += [(n, it, {}) for n, it in entry.EXTRA_BUILDS]
   unique = []
