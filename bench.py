@@ -213,8 +213,12 @@ def main():
   if not torch.cuda.is_available():
     sys.exit('bench.py: no CUDA device; this backend has no CPU path')
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-  torch.cuda.set_device(local_rank)
   distributed = world > 1
+  # one process per GPU: keep each on its GPU's NUMA node, or the end-to-end
+  # leg's host buffers of half the ranks sit across the socket interconnect
+  # (one rank keeps every core: the CPU baseline runs on all of them)
+  numa_node = soda_cuda.bind_host_to_gpu(local_rank) if distributed else None
+  torch.cuda.set_device(local_rank)
   if distributed:
     import torch.distributed as dist
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -339,7 +343,9 @@ def main():
               'h2d_ms': e2e_stats['h2d_ms'], 'd2h_ms': e2e_stats['d2h_ms'],
               'kernel_ms': e2e_stats['kernel_ms'], 'steps': e2e_steps,
               'api': 'soda_cuda_run (C ABI form of jacobi2d(buffer_t*, '
-                     'buffer_t*, const char*)), pinned host buffers'},
+                     'buffer_t*, const char*)), pinned host buffers; one '
+                     'independent 16384 x 16384 run per GPU',
+              'numa_node_rank0': numa_node},
       'gpu_launches': launches_per_step * args.steps,
       'roofline': {
           'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',

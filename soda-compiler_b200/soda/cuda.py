@@ -448,6 +448,48 @@ class Library:
     return value
 
 
+def bind_host_to_gpu(device_index):
+  """Run this process on the CPUs of the NUMA node GPU ``device_index``
+  hangs off, so that host buffers allocated from now on (first touch, pinned
+  or not) sit on that node and host<->device copies do not cross the socket
+  interconnect.  Matters with one process per GPU on a two-socket box, where
+  an unbound process may land on the far socket.  Returns the node, or None
+  when the topology is not exposed (virtualised PCI) — then nothing changes.
+  """
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+    index = device_index
+    if visible:
+      entry = visible.split(',')[device_index].strip()
+      if entry.isdigit():
+        index = int(entry)
+    bus = pynvml.nvmlDeviceGetPciInfo(
+        pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+    bus = bus.decode() if isinstance(bus, bytes) else bus
+    bus = bus.lower()
+    if len(bus.split(':')[0]) == 8:      # NVML pads the domain to 8 digits
+      bus = bus[4:]
+    with open('/sys/bus/pci/devices/%s/numa_node' % bus) as handle:
+      node = int(handle.read())
+    if node < 0:
+      return None
+    with open('/sys/devices/system/node/node%d/cpulist' % node) as handle:
+      text = handle.read().strip()
+    cpus = set()
+    for part in text.split(','):
+      first, _, last = part.partition('-')
+      cpus.update(range(int(first), int(last or first) + 1))
+    cpus &= os.sched_getaffinity(0)
+    if not cpus:
+      return None
+    os.sched_setaffinity(0, cpus)
+    return node
+  except Exception:   # pylint: disable=broad-except
+    return None
+
+
 _loaded = {}
 
 
