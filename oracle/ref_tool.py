@@ -26,6 +26,10 @@ Commands
       (host.print_test, src/soda/codegen/xilinx/host.py:984-1167) preceded only
       by the includes it needs and the ``error_report`` declaration of
       host.py:46.
+  host FILE [--iterate N]
+      The reference's complete generated OpenCL host file on stdout
+      (host.print_code): the source of the FPGA wire-format loops that
+      oracle/fpga_layout_ref.py extracts.
 """
 import argparse
 import collections
@@ -48,16 +52,19 @@ def _import_reference():
   sys.path[:0] = [os.path.join(HERE, 'refshim'), REFERENCE_SRC]
 
 
-def load_stencil(path, iterate=None):
-  """What src/sodac:80-123 does, without the CLI."""
+def load_stencil(path, iterate=None, tile_size=None, burst_width=None):
+  """What src/sodac:80-123 does, without the CLI (``--tile-size`` and
+  ``--burst-width`` override the program's, :94-110)."""
   import textx
   from soda import core, grammar
   with open(path) as handle:
     model = textx.metamodel_from_str(
         grammar.GRAMMAR, classes=grammar.CLASSES).model_from_str(handle.read())
-  tile_size = list(model.tile_size[:model.dim - 1]) + [0]
+  override = list(tile_size or [])
+  tile_size = [override[d] if d < len(override) and override[d] > 0
+               else model.tile_size[d] for d in range(model.dim - 1)] + [0]
   return core.Stencil(
-      burst_width=model.burst_width,
+      burst_width=burst_width or model.burst_width,
       iterate=model.iterate if iterate is None else iterate,
       dram_in=None, dram_out=None, app_name=model.app_name,
       input_stmts=model.input_stmts, param_stmts=model.param_stmts,
@@ -119,21 +126,33 @@ def write_harness(stencil, outdir):
     handle.write(body.getvalue())
 
 
+def write_host(stencil, out):
+  """The reference's complete generated OpenCL host file (host.print_code,
+  src/soda/codegen/xilinx/host.py:1169-1204), verbatim."""
+  from soda.codegen.xilinx import host
+  host.print_code(stencil, out)
+
+
 def main():
   parser = argparse.ArgumentParser(description=__doc__.split('\n')[0])
   sub = parser.add_subparsers(dest='command', required=True)
-  for name in ('describe', 'harness'):
+  for name in ('describe', 'harness', 'host'):
     cmd = sub.add_parser(name)
     cmd.add_argument('soda_file')
     cmd.add_argument('--iterate', type=int)
+    cmd.add_argument('--tile-size', type=int, nargs='+')
+    cmd.add_argument('--burst-width', type=int)
     if name == 'harness':
       cmd.add_argument('--outdir', required=True)
   args = parser.parse_args()
   _import_reference()
-  stencil = load_stencil(args.soda_file, args.iterate)
+  stencil = load_stencil(args.soda_file, args.iterate, args.tile_size,
+                         args.burst_width)
   if args.command == 'describe':
     json.dump(describe(stencil), sys.stdout, indent=1)
     sys.stdout.write('\n')
+  elif args.command == 'host':
+    write_host(stencil, sys.stdout)
   else:
     write_harness(stencil, args.outdir)
 

@@ -1,0 +1,99 @@
+"""FPGA wire format without a GPU: the layout constants and the
+numpy oracle against fixtures produced by the unmodified reference's own
+generated loops (oracle/fpga_layout_ref.py --fixtures)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import common
+import fpga_layout as oracle_layout      # oracle/fpga_layout.py
+from soda import core, fpga_layout
+
+FIXTURES = sorted(glob.glob(os.path.join(common.GOLDEN_DIR, 'fpga_layout',
+                                         '*.npz')))
+
+
+def load(path):
+  data = np.load(path)
+  name = os.path.basename(path).split('_')[0]
+  banks = [[int(b) for b in row if b >= 0] for row in data['banks']]
+  stencil = core.Stencil.from_text(
+      common.bench_text(name), tile_size=[int(t) for t in data['tile_size']],
+      burst_width=int(data['burst_width']))
+  tensors = list(stencil.input_stmts) + list(stencil.output_stmts)
+  for stmt, dram in zip(tensors, banks):
+    stmt.dram = tuple(dram)
+  dims = tuple(int(n) for n in data['dims'])
+  return data, stencil, fpga_layout.WireLayout(stencil, dims)
+
+
+def test_fixtures_exist():
+  assert len(FIXTURES) >= 4
+
+
+@pytest.mark.parametrize('path', FIXTURES, ids=os.path.basename)
+def test_layout_constants_match_the_reference(path):
+  data, stencil, layout = load(path)
+  assert list(layout.tile_num) == data['tile_num'].tolist()
+  assert [layout.tile_size_linearized_i, layout.tile_size_linearized_o] == \
+      data['tile_size_linearized'].tolist()
+  names = list(stencil.input_names) + list(stencil.output_names)
+  widths = [layout.descriptor(n).elem_size for n in names]
+  assert [layout.bank_elems(n) * w for n, w in zip(names, widths)] == \
+      data['bank_bytes'].tolist()
+
+
+@pytest.mark.parametrize('path', FIXTURES, ids=os.path.basename)
+def test_oracle_pack_and_unpack_match_the_reference(path):
+  data, stencil, layout = load(path)
+  for k, name in enumerate(stencil.input_names):
+    want = [data['in%d_bank%d' % (k, b)] for b in range(4)]
+    got = [np.zeros_like(w) for w in want]
+    oracle_layout.pack(layout, name, data['in%d' % k], got)
+    for b in range(4):
+      common.assert_bit_exact(got[b], want[b], '%s bank %d' % (name, b))
+    assert any(g.any() for g in got)
+  for k, name in enumerate(stencil.output_names):
+    banks = [data['out%d_bank%d' % (k, b)] for b in range(4)]
+    got = np.zeros_like(data['out%d' % k])
+    oracle_layout.unpack(layout, name, got, banks)
+    common.assert_bit_exact(got, data['out%d' % k], name)
+    assert got.any()
+
+
+def test_tile_smaller_than_the_window_is_rejected():
+  from haoda import util
+  stencil = core.Stencil.from_text(common.bench_text('blur'), tile_size=[2])
+  with pytest.raises(util.SemanticError):
+    fpga_layout.WireLayout(stencil, (64, 8))
+
+
+def test_configuration_the_reference_overruns_is_rejected():
+  """4 input banks, 1 output bank: the output tiles (sized from the input's
+  burst count, host.py:334-347) are shorter than their cell count and the
+  last one ends beyond the buffer of host.py:399-415."""
+  from haoda import util
+  stencil = core.Stencil.from_text(common.bench_text('jacobi3d'),
+                                   tile_size=[40, 17], burst_width=128)
+  stencil.input_stmts[0].dram = (0, 1, 2, 3)
+  stencil.output_stmts[0].dram = (1,)
+  layout = fpga_layout.WireLayout(stencil, (100, 40, 23))
+  layout.descriptor(stencil.input_names[0])
+  with pytest.raises(util.SemanticError, match='beyond the bank buffer'):
+    layout.descriptor(stencil.output_names[0])
+
+
+def test_library_exports_the_declared_entry_points():
+  import ctypes
+  import re
+  header = os.path.join(common.ROOT, 'include', 'soda_fpga_layout.h')
+  with open(header) as handle:
+    text = re.sub(r'/\*.*?\*/', '', handle.read(), flags=re.S)
+  names = sorted(set(re.findall(r'\b(soda_fpga_\w+)\s*\(', text)))
+  assert names == ['soda_fpga_pack', 'soda_fpga_unpack']
+  lib = ctypes.CDLL(fpga_layout.build())
+  for name in names:
+    assert hasattr(lib, name)
+  assert ctypes.sizeof(fpga_layout.TensorLayout) == 144
