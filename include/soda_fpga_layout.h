@@ -42,12 +42,21 @@ typedef struct soda_fpga_layout_t {
                                868-877); inputs: 0 */
 } soda_fpga_layout_t;
 
-/* dense (device) -> bank buffers (device, indexed by bank id 0..3; unused
- * banks may be NULL).  reference host.py:629-686. */
+/* The function picks the direction, the descriptor the mapping.  With an
+ * input's descriptor soda_fpga_pack is the reference host's input loop nest
+ * (host.py:629-686) and soda_fpga_unpack its inverse (what a stand-in for the
+ * FPGA kernel does first); with an output's descriptor soda_fpga_unpack is
+ * the host's output loop nest (host.py:823-901) and soda_fpga_pack its
+ * inverse (what the stand-in does last).
+ *
+ * dense (device) -> bank buffers (device, indexed by bank id 0..3; unused
+ * banks may be NULL). */
 int soda_fpga_pack(const soda_fpga_layout_t* layout, const void* dense,
                    void* const* banks, void* stream);
 
-/* bank buffers -> the valid cells of dense.  reference host.py:823-901. */
+/* bank buffers -> the cells of dense the mapping covers.  Where the cell
+ * ranges of neighbouring tiles overlap, the later tile's value is taken, as
+ * the reference's ascending tile loops leave it. */
 int soda_fpga_unpack(const soda_fpga_layout_t* layout, void* dense,
                      const void* const* banks, void* stream);
 

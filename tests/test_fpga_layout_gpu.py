@@ -89,3 +89,40 @@ def test_kernels_match_the_oracle(name, tile, burst, dims, banks):
                        {b: _to_device(bank_arrays[b]) for b in stmt.dram})
     torch.cuda.synchronize()
     common.assert_bit_exact(_to_host(dense, want), want, stmt.name)
+
+
+def test_both_mappings_run_in_both_directions():
+  """The function picks the direction, the descriptor the mapping: a GPU
+  stand-in for the FPGA kernel reads its inputs OUT of the input mapping and
+  writes its outputs INTO the output mapping.  Round trips return the data."""
+  stencil = core.Stencil.from_text(common.bench_text('heat3d'),
+                                   tile_size=[24, 20], burst_width=256)
+  stencil.input_stmts[0].dram = (0, 2)
+  stencil.output_stmts[0].dram = (1, 3)
+  dims = (61, 50, 11)
+  layout = fpga_layout.WireLayout(stencil, dims)
+  rng = np.random.default_rng(5)
+  shape = tuple(reversed(dims))
+  dense = (rng.random(shape) * 1000).astype(np.float32)
+  name_in, name_out = stencil.input_names[0], stencil.output_names[0]
+  # input mapping: every cell of the grid is in some tile
+  banks = {b: torch.zeros(layout.bank_elems(name_in), dtype=torch.int32,
+                          device='cuda') for b in layout.banks(name_in)}
+  fpga_layout.pack(layout, name_in, _to_device(dense), banks)
+  back = torch.zeros(shape, dtype=torch.int32, device='cuda')
+  fpga_layout.unpack(layout, name_in, back, banks)
+  torch.cuda.synchronize()
+  common.assert_bit_exact(_to_host(back, dense), dense, 'input mapping')
+  # output mapping: the cells whose window fits come back, the rest is kept
+  banks = {b: torch.zeros(layout.bank_elems(name_out), dtype=torch.int32,
+                          device='cuda') for b in layout.banks(name_out)}
+  fpga_layout.pack(layout, name_out, _to_device(dense), banks)
+  back = torch.full(shape, 77, dtype=torch.int32, device='cuda')
+  fpga_layout.unpack(layout, name_out, back, banks)
+  torch.cuda.synchronize()
+  want = np.full(shape, 77, np.int32).view(np.float32)
+  lo, hi = layout.window_offset, layout.valid_hi_margin()
+  inner = tuple(slice(l, n - h) for l, h, n in
+                reversed(list(zip(lo, hi, dims))))
+  want[inner] = dense[inner]
+  common.assert_bit_exact(_to_host(back, dense), want, 'output mapping')
