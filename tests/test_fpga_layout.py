@@ -97,3 +97,51 @@ def test_library_exports_the_declared_entry_points():
   for name in names:
     assert hasattr(lib, name)
   assert ctypes.sizeof(fpga_layout.TensorLayout) == 144
+
+
+@pytest.mark.parametrize('path', FIXTURES, ids=os.path.basename)
+def test_kernel_index_arithmetic_model_matches_the_reference(path):
+  """tests/wire_kernel_model.py restates the CUDA kernel's decomposition and
+  index arithmetic; it must reproduce the reference's fixtures too."""
+  import wire_kernel_model as model
+  data, stencil, layout = load(path)
+  for k, name in enumerate(stencil.input_names):
+    want = [data['in%d_bank%d' % (k, b)] for b in range(4)]
+    got = {b: np.zeros_like(want[b]) for b in range(4)}
+    model.run(layout.descriptor(name), data['in%d' % k].ravel(), got, True)
+    for b in range(4):
+      common.assert_bit_exact(got[b], want[b], '%s bank %d' % (name, b))
+  for k, name in enumerate(stencil.output_names):
+    banks = {b: data['out%d_bank%d' % (k, b)] for b in range(4)}
+    got = np.zeros_like(data['out%d' % k])
+    model.run(layout.descriptor(name), got.reshape(-1), banks, False)
+    common.assert_bit_exact(got, data['out%d' % k], name)
+
+
+def test_kernel_model_round_trips_both_mappings():
+  import wire_kernel_model as model
+  stencil = core.Stencil.from_text(common.bench_text('heat3d'),
+                                   tile_size=[24, 20], burst_width=256)
+  stencil.input_stmts[0].dram = (0, 2)
+  stencil.output_stmts[0].dram = (1, 3)
+  dims = (61, 50, 11)
+  layout = fpga_layout.WireLayout(stencil, dims)
+  shape = tuple(reversed(dims))
+  dense = (np.random.default_rng(5).random(shape) * 1000).astype(np.float32)
+  name_in, name_out = stencil.input_names[0], stencil.output_names[0]
+  banks = {b: np.zeros(layout.bank_elems(name_in), np.float32)
+           for b in range(4)}
+  model.run(layout.descriptor(name_in), dense.ravel(), banks, True)
+  back = np.zeros(shape, np.float32)
+  model.run(layout.descriptor(name_in), back.reshape(-1), banks, False)
+  common.assert_bit_exact(back, dense, 'input mapping')
+  banks = {b: np.zeros(layout.bank_elems(name_out), np.float32)
+           for b in range(4)}
+  model.run(layout.descriptor(name_out), dense.ravel(), banks, True)
+  back = np.full(shape, 77, np.float32)
+  model.run(layout.descriptor(name_out), back.reshape(-1), banks, False)
+  want = np.full(shape, 77, np.float32)
+  inner = tuple(slice(l, n - h) for l, h, n in reversed(list(zip(
+      layout.window_offset, layout.valid_hi_margin(), dims))))
+  want[inner] = dense[inner]
+  common.assert_bit_exact(back, want, 'output mapping')
