@@ -19,10 +19,11 @@ from soda.codegen import cuda as codegen          # noqa: E402
 
 
 def build(job):
+  """job: (benchmark name, iterate, options) or (label, stencil, options)."""
   name, iterate, options = job
   options = dict(options)
   fast = bool(options.pop('fast', 0))
-  stencil = core.Stencil.from_file(
+  stencil = iterate if hasattr(iterate, 'app_name') else core.Stencil.from_file(
       os.path.join(ROOT, 'benchmarks', name + '.soda'), iterate=iterate)
   return soda_cuda.build(stencil, fast_math=fast,
                          options=codegen.Options(**options))
@@ -33,7 +34,7 @@ def main():
   if '--clean' in args:
     args.remove('--clean')
     shutil.rmtree(soda_cuda.DEFAULT_BUILD_DIR, ignore_errors=True)
-  jobs = []
+  jobs, untuned = [], []
   if args:
     import quick_bench
     for text in args:
@@ -61,24 +62,40 @@ def main():
       jobs.append((name, iterate, options))
     import test_types_gpu
     for name, _, options in test_types_gpu.CASES:
-      print('%-40s %s' % ((name, options), os.path.relpath(soda_cuda.build(
-          test_types_gpu.stencil_of(name),
-          options=codegen.Options(**options)), ROOT)))
+      jobs.append((name, test_types_gpu.stencil_of(name), options))
     import param_programs
     for name, _, options in param_programs.CASES:
-      print('%-40s %s' % ((name, options), os.path.relpath(soda_cuda.build(
-          param_programs.stencil_of(name),
-          options=codegen.Options(**options)), ROOT)))
+      jobs.append((name, param_programs.stencil_of(name), options))
+    import test_fastmath_gpu
+    for name, iterate, _ in test_fastmath_gpu.CASES:
+      jobs.append((name, iterate, {'fast': 1}))
+    import test_fullsize_gpu
+    for name, iterate, _, _ in test_fullsize_gpu.CONFIGS:
+      jobs.append((name, iterate, {}))
+    # the autotuner test times the planner's own choices, not tuned.json's
+    import test_tune_gpu
+    marks = [m for m in test_tune_gpu.test_tune_times_every_candidate
+             .pytestmark if m.name == 'parametrize']
+    for name, iterate, _, option_sets in marks[0].args[1]:
+      untuned += [(name, iterate, options) for options in option_sets]
     jobs += [(n, None, {}) for n in entry.BENCHMARKS]
     jobs += [(n, it, {}) for n, it in entry.EXTRA_BUILDS]
-  unique = []
-  for job in jobs:
-    key = (job[0], job[1], sorted(job[2].items()))
-    if key not in [(j[0], j[1], sorted(j[2].items())) for j in unique]:
-      unique.append(job)
-  with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
-    for job, path in zip(unique, pool.map(build, unique)):
-      print('%-40s %s' % (job, os.path.relpath(path, ROOT)))
+
+  def label(job):
+    stencil = job[1] if hasattr(job[1], 'app_name') else None
+    return (job[0], stencil.iterate if stencil else job[1],
+            sorted(job[2].items()))
+  for group, env in ((jobs, None), (untuned, '0')):
+    unique = []
+    for job in group:
+      if label(job) not in [label(j) for j in unique]:
+        unique.append(job)
+    if env is not None:
+      os.environ['SODA_CUDA_TUNED'] = env
+    with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
+      for job, path in zip(unique, pool.map(build, unique)):
+        print('%-40s %s' % (label(job), os.path.relpath(path, ROOT)))
+    os.environ.pop('SODA_CUDA_TUNED', None)
 
 
 if __name__ == '__main__':
