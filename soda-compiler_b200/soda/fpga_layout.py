@@ -26,6 +26,7 @@ written for an xclbin, a capture of its DMA buffers — can enter and leave the
 GPU backend without a CPU repacking pass.  Pure byte movement: HBM-bound.
 """
 import ctypes
+import hashlib
 import os
 import shutil
 import subprocess
@@ -36,7 +37,7 @@ from soda import core
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(_PKG_ROOT, 'csrc', 'soda_fpga_layout.cu')
 INCLUDE_DIR = os.path.join(os.path.dirname(_PKG_ROOT), 'include')
-LIB_PATH = os.path.join(_PKG_ROOT, '_build', 'libsoda_fpga_layout.so')
+HEADER = os.path.join(INCLUDE_DIR, 'soda_fpga_layout.h')
 MAX_DRAM_BANK = 4     # reference src/soda/util.py MAX_DRAM_BANK
 
 
@@ -212,10 +213,21 @@ def _serialize(vec, tile_size):
 
 # --- the CUDA side ---------------------------------------------------------------
 
+def lib_path():
+  """In-tree, named by the hash of its sources (travels with the snapshot to
+  GPU machines; file times do not survive that trip)."""
+  digest = hashlib.sha256()
+  for path in (CSRC, HEADER):
+    with open(path, 'rb') as handle:
+      digest.update(handle.read())
+  return os.path.join(_PKG_ROOT, '_build', 'fpga_layout-%s' %
+                      digest.hexdigest()[:12], 'libsoda_fpga_layout.so')
+
+
 def build(force=False):
   """Compile csrc/soda_fpga_layout.cu for sm_100a (in-tree, cached)."""
-  if os.path.exists(LIB_PATH) and not force and \
-      os.path.getmtime(LIB_PATH) >= os.path.getmtime(CSRC):
+  LIB_PATH = lib_path()
+  if os.path.exists(LIB_PATH) and not force:
     return LIB_PATH
   if shutil.which('nvcc') is None:
     raise RuntimeError('nvcc not found: the wire-format kernels are CUDA only')
