@@ -139,6 +139,36 @@ def test_chunking_does_not_change_results(monkeypatch):
     common.assert_bit_exact(got[0], want[0], 'chunks=' + chunks)
 
 
+@pytest.mark.parametrize('name,iterate,dims', [
+    ('heat3d', 2, (128, 64, 90)), ('jacobi2d', 8, (2048, 700))])
+def test_a_run_cut_at_block_boundaries_is_the_same_run(name, iterate, dims):
+  """soda_cuda_chunk_rows + soda_cuda_launch_chunked (what the multi-GPU
+  slab runner builds its face and interior launches from): first block,
+  last block and the rest, on three streams, equal the one-launch run."""
+  import torch
+  library = _library(name, iterate, {'depth': iterate})
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=13)
+  want = orc.run(inputs)
+  dev_in = [torch.from_numpy(a).cuda() for a in inputs]
+  dev_out = [torch.full_like(dev_in[0], 123.0)]
+  rows = dims[-1]
+  chunk = library.chunk_rows(iterate, dims, rows)
+  assert 1 <= chunk <= rows and library.lead_rows(iterate) > 0
+  if 2 * chunk >= rows:
+    chunk = max(1, rows // 4)      # any cut works; keep three pieces
+  region = library.valid_region(dims, iterate)
+  lo, hi = [r[0] for r in region], [r[1] for r in region]
+  torch.cuda.synchronize()
+  streams = [torch.cuda.Stream() for _ in range(3)]
+  pieces = [(0, chunk), (rows - chunk, rows), (chunk, rows - chunk)]
+  for stream, (r0, r1) in zip(streams, pieces):
+    library.launch(iterate, dev_in, dev_out, dims, r0, r1, lo, hi,
+                   stream.cuda_stream, chunk)
+  torch.cuda.synchronize()
+  common.assert_bit_exact(dev_out[0].cpu().numpy(), want[0], name)
+
+
 REF_CASES = [('blur', 1, (2000, 1000)), ('sobel2d', 1, (1101, 157)),
              ('jacobi2d', 3, (1536, 200)), ('seidel2d', 2, (999, 130)),
              ('denoise2d', 1, (1024, 128)), ('jacobi3d', 2, (128, 64, 40)),

@@ -58,6 +58,11 @@ def main():
       jobs.append((name, iterate, options))
     for name, iterate, _ in test_parity_gpu.REF_CASES:
       jobs.append((name, iterate, {}))
+    marks = [m for m in
+             test_parity_gpu.test_a_run_cut_at_block_boundaries_is_the_same_run
+             .pytestmark if m.name == 'parametrize']
+    for name, iterate, _ in marks[0].args[1]:
+      jobs.append((name, iterate, {'depth': iterate}))
     for name, iterate, options, *_ in test_slab_gpu.CASES:
       jobs.append((name, iterate, options))
     import test_types_gpu
