@@ -43,6 +43,7 @@ sys.path[:0] = [os.path.join(ROOT, 'soda-compiler_b200')]
 WORKLOAD = dict(program='jacobi2d', iterate=64, dims=(16384, 16384))
 BYTES_PER_CELL = 8          # float32 in + float32 out
 CPU_SAMPLE_ITERATE = 64     # iterations timed on the CPU: the whole workload
+CPU_SINGLE_THREAD_ITERATE = 4   # ... and on one thread (SURVEY.md 8d asks for both)
 HBM_FALLBACK_GBS = 6650.0   # B200_PROFILING.md, if MEASURED_PEAKS.json absent
 
 
@@ -143,6 +144,13 @@ def cpu_port_gcells(iterate, threads=None):
   if threads:
     os.environ['OMP_NUM_THREADS'] = str(threads)
   oracle = golden.Oracle(load_stencil(iterate))
+  if threads:
+    # the environment only counts before libgomp starts; afterwards ask it
+    try:
+      import ctypes
+      ctypes.CDLL('libgomp.so.1').omp_set_num_threads(int(threads))
+    except OSError:
+      pass
   inputs = oracle.reference_inputs(WORKLOAD['dims'])
   _, seconds = oracle.run(inputs, with_seconds=True)
   cells = WORKLOAD['dims'][0] * WORKLOAD['dims'][1]
@@ -369,6 +377,12 @@ def main():
         'sample': '%dx%d float32, %d of %d iterations (same grid, ping-pong '
                   'golden loop, g++ -O3 -fopenmp)' % (
                       dims + (CPU_SAMPLE_ITERATE, iterate))}
+    one_value, one_seconds = cpu_port_gcells(CPU_SINGLE_THREAD_ITERATE, 1)
+    result['cpu_baseline']['single_thread'] = {
+        'value': one_value, 'unit': 'GCell/s', 'cores': 1,
+        'seconds': one_seconds,
+        'sample': '%d of %d iterations' % (CPU_SINGLE_THREAD_ITERATE,
+                                           iterate)}
   print(json.dumps(result))
   if distributed:
     dist.destroy_process_group()
