@@ -21,7 +21,9 @@ depth, the block shape, the vector width and the depth of the input queue
    gives no options of its own (SODA_CUDA_TUNED=0 disables the table).
 """
 import concurrent.futures
+import contextlib
 import itertools
+import os
 
 import numpy as np
 
@@ -34,6 +36,21 @@ from soda.codegen.cuda import tuned
 signature = tuned.signature
 record = tuned.record
 load_table = tuned.load_table
+
+
+@contextlib.contextmanager
+def untuned():
+  """Inside, an empty option set means the planner's own choice, not the
+  winner of an earlier tuning run."""
+  before = os.environ.get('SODA_CUDA_TUNED')
+  os.environ['SODA_CUDA_TUNED'] = '0'
+  try:
+    yield
+  finally:
+    if before is None:
+      del os.environ['SODA_CUDA_TUNED']
+    else:
+      os.environ['SODA_CUDA_TUNED'] = before
 
 
 def _accepts(program, options):
@@ -49,6 +66,11 @@ def _accepts(program, options):
 def candidates(program, limit=32):
   """Option sets (``codegen.Options`` keyword dicts) worth timing, the
   planner's own choice first."""
+  with untuned():
+    return _candidates(program, limit)
+
+
+def _candidates(program, limit):
   # the planner's depth with every block/queue geometry, then the other
   # depths with the planner's geometry (a full product is mostly compile time)
   depths = []
@@ -91,7 +113,8 @@ def build_all(stencil, option_sets, jobs=8, fast_math=False):
                                       options=codegen.Options(**options))
     except Exception as e:   # pylint: disable=broad-except
       return options, e
-  with concurrent.futures.ThreadPoolExecutor(max_workers=jobs) as pool:
+  with untuned(), concurrent.futures.ThreadPoolExecutor(
+      max_workers=jobs) as pool:
     return list(pool.map(one, option_sets))
 
 

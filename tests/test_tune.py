@@ -47,6 +47,11 @@ def test_tuned_table_steers_the_planner(tmp_path, monkeypatch):
   assert entry['gcell_per_s'] == round(4096 * 4096 * 64 / 1.25 / 1e6, 1)
   tuned_sched = codegen.make_schedules(program)[0]
   assert (tuned_sched.depth, tuned_sched.threads) == (4, 64)
+  # while tuning, an empty option set is the planner's choice again
+  with cuda_tune.untuned():
+    assert codegen.make_schedules(program)[0].depth == 8
+  assert codegen.make_schedules(program)[0].depth == 4
+  assert {'depth': 4} in cuda_tune.candidates(program)   # distinct from {}
   # explicit options win over the table; the switch turns it off
   assert codegen.make_schedules(
       program, codegen.Options(depth=2))[0].depth == 2
