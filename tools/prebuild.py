@@ -71,6 +71,9 @@ def main():
     import param_programs
     for name, _, options in param_programs.CASES:
       jobs.append((name, param_programs.stencil_of(name), options))
+    import wide_type_programs
+    for name, _, options in wide_type_programs.CASES:
+      jobs.append((name, wide_type_programs.stencil_of(name), options))
     import test_fastmath_gpu
     for name, iterate, _ in test_fastmath_gpu.CASES:
       jobs.append((name, iterate, {'fast': 1}))
