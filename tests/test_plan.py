@@ -126,6 +126,70 @@ def test_random_programs_schedule_correctly(generated, prefetch):
   sim.check_outputs(sched, dims, outs)
 
 
+# --- the register-streaming family (the default kernels) ----------------------
+
+REG_CASES = [
+    ('blur', 1, (300, 23)), ('sobel2d', 1, (300, 23)),
+    ('jacobi2d', 1, (300, 23)), ('jacobi2d', 8, (300, 60)),   # paired f32x2
+    ('jacobi2d', 6, (300, 47)), ('jacobi2d', 3, (300, 30)),   # odd: unpaired
+    ('seidel2d', 2, (300, 23)), ('denoise2d', 1, (300, 23)),
+    ('heat3d', 2, (140, 40, 12)), ('heat3d', 1, (140, 40, 9)),
+    ('jacobi3d', 2, (140, 40, 12)), ('denoise3d', 1, (140, 20, 9)),
+]
+
+
+@pytest.mark.parametrize('name,depth,dims', REG_CASES)
+def test_register_schedule_produces_the_valid_region(name, depth, dims,
+                                                     monkeypatch):
+  """reg_schedule_sim executes plan.RegSchedule — register histories, warp
+  shuffles, shared planes for y neighbours, paired lanes, trips — as the
+  emitter lays it out."""
+  import reg_schedule_sim as reg_sim
+  monkeypatch.setenv('SODA_CUDA_TUNED', '0')
+  program = plan.extract_program(common.stencil(name, depth))
+  sched = codegen.make_schedules(program, codegen.Options(depth=depth))[0]
+  assert sched.style == 'reg' and sched.depth == depth
+  for chunk in (7, dims[-1]):
+    outs = reg_sim.run_schedule(sched, dims, chunk)
+    reg_sim.check_outputs(sched, dims, outs)
+
+
+def test_register_schedule_sim_notices_a_wrong_schedule(monkeypatch):
+  import reg_schedule_sim as reg_sim
+  monkeypatch.setenv('SODA_CUDA_TUNED', '0')
+  for name, depth, dims, attr in (('jacobi2d', 8, (300, 60), 'pair_lag'),
+                                  ('blur', 1, (300, 23), 'lead')):
+    program = plan.extract_program(common.stencil(name, depth))
+    sched = codegen.make_schedules(program, codegen.Options(depth=depth))[0]
+    setattr(sched, attr, getattr(sched, attr) + (1 if attr == 'pair_lag'
+                                                 else -1))
+    with pytest.raises(AssertionError):
+      outs = reg_sim.run_schedule(sched, dims, 7)
+      reg_sim.check_outputs(sched, dims, outs)
+
+
+@settings(max_examples=20, deadline=None)
+@given(random_program())
+def test_random_programs_schedule_correctly_in_registers(generated):
+  import reg_schedule_sim as reg_sim
+  text, dim, iterate = generated
+  stencil = core.Stencil.from_text(text)
+  program = plan.extract_program(stencil)
+  program.check_windows()
+  dims = (300, 29) if dim == 2 else (140, 40, 13)
+  try:
+    sched = codegen.make_schedule(program, iterate,
+                                  codegen.Options(style='reg'))
+  except Exception as e:   # pylint: disable=broad-except
+    # a legal refusal: halo larger than the tile, histories too large
+    assert any(word in str(e) for word in ('halo', 'shared memory', 'tile',
+                                           'register')), str(e)
+    return
+  assert sched.style == 'reg'
+  outs = reg_sim.run_schedule(sched, dims, 9)
+  reg_sim.check_outputs(sched, dims, outs)
+
+
 def test_window_without_store_point_is_rejected():
   text = ('kernel: k\nburst width: 64\nunroll factor: 1\niterate: 1\n'
           'input float: a(8, *)\nlocal float: l(0, 0) = a(0, -1)\n'
