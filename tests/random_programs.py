@@ -1,0 +1,66 @@
+"""Seeded random SODA programs (shared by the CPU compile test, the prebuild
+tool and the GPU parity test): 2-D and 3-D, 1-4 iterations, up to four
+stages with up to four neighbour reads each, tensors of one of six types with
+an occasional stage of another width.
+
+Integer programs only add, subtract and scale by small literals: the golden
+loop evaluates them in C++ `int`, where overflow is undefined, and operands
+read back from 8/16-bit tensors keep such sums far from it.  32-bit integers
+are unsigned (wrap-around is defined).
+"""
+import random
+
+from soda import core
+
+KINDS = ('float', 'float', 'int16', 'uint8', 'double', 'uint32')
+OTHER = {'float': 'double', 'double': 'float', 'int16': 'int32',
+         'uint8': 'uint16', 'uint32': 'uint16'}
+SEEDS = tuple(range(8))
+
+
+def program_text(seed):
+  rng = random.Random(seed)
+  dim = rng.choice((2, 2, 3))
+  kind = rng.choice(KINDS)
+  floating = kind in ('float', 'double')
+  n_local = rng.randint(0, 3)
+  names = ['a']
+  lines = ['kernel: rnd%d' % seed, 'burst width: 64', 'unroll factor: 1',
+           'input %s: a(%s*)' % (kind, ''.join('8, ' for _ in range(dim - 1)))]
+  zero = ', '.join('0' for _ in range(dim))
+  for k in range(n_local + 1):
+    target = 'l%d' % k if k < n_local else 'out'
+    text = ''
+    for _ in range(rng.randint(1, 3)):
+      parent = rng.choice(names)
+      off = [rng.randint(-2, 2) for _ in range(dim)]
+      ref = '%s(%s)' % (parent, ', '.join(map(str, off)))
+      if floating:
+        text += ref + rng.choice((' + ', ' - ', ' * '))
+      else:
+        scale = rng.choice(('', '', ' * 2', ' * 3'))
+        text += ref + scale + rng.choice((' + ', ' - '))
+    # every window must contain the store point (Program.check_windows)
+    text += '%s(%s)' % (names[-1], zero)
+    if rng.random() < 0.3:
+      text = '(%s)%s' % (text, {'float': ' * 0.25f', 'double': ' / 3.0'}.get(
+          kind, ' / 3'))
+    stage_type = kind
+    if k < n_local and rng.random() < 0.2:
+      stage_type = OTHER[kind]
+    lines.append('%s %s: %s(%s) = %s' % (
+        'local' if k < n_local else 'output', stage_type, target, zero, text))
+    names.append(target)
+  lines.append('iterate: %d' % rng.randint(1, 4))
+  return '\n'.join(lines) + '\n'
+
+
+def stencil_of(seed):
+  return core.Stencil.from_text(program_text(seed))
+
+
+def dims_of(stencil, seed):
+  rng = random.Random(1000 + seed)
+  if stencil.dim == 2:
+    return (rng.choice((1024, 1061, 2048)), rng.randint(90, 200))
+  return (rng.choice((128, 131, 256)), rng.randint(35, 64), rng.randint(30, 48))

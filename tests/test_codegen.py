@@ -132,3 +132,31 @@ backend.print_kernel(program, backend.make_schedules(program), sys.stdout)
                  '--cuda-kernel', '-')
     assert ours.returncode == 0
     assert via_reference.stdout == ours.stdout
+
+
+def test_random_programs_emit_code_nvcc_accepts(tmp_path, monkeypatch):
+  """Beyond the benchmarks: the kernels emitted for seeded random programs
+  (mixed types, 2-D/3-D, fused iterations) compile for sm_100a, and the
+  oracle of each builds and runs."""
+  import subprocess
+  import numpy as np
+  import golden
+  import random_programs as rp
+  from soda import cuda as soda_cuda
+  monkeypatch.setenv('SODA_CUDA_TUNED', '0')
+  for seed in rp.SEEDS[:4]:
+    stencil = rp.stencil_of(seed)
+    _, kernel, _ = soda_cuda.generate_sources(stencil)
+    path = tmp_path / ('k%d.cu' % seed)
+    path.write_text(kernel)
+    done = subprocess.run(
+        ['nvcc'] + soda_cuda.ARCH_FLAGS + [
+            '-std=c++17', '-fmad=false', '-I', soda_cuda.CSRC_DIR, '-I',
+            soda_cuda.INCLUDE_DIR, '-c', str(path), '-o',
+            str(tmp_path / 'k.o')],
+        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert done.returncode == 0, rp.program_text(seed) + done.stdout[-2000:]
+    orc = golden.Oracle(stencil)
+    dims = (40, 30) if stencil.dim == 2 else (24, 20, 18)
+    out = orc.run(common.random_inputs(orc, dims, seed=seed))
+    assert out[0].shape == tuple(reversed(dims))

@@ -71,6 +71,9 @@ def main():
     import param_programs
     for name, _, options in param_programs.CASES:
       jobs.append((name, param_programs.stencil_of(name), options))
+    import random_programs
+    for seed in random_programs.SEEDS:
+      jobs.append(('rnd%d' % seed, random_programs.stencil_of(seed), {}))
     import wide_type_programs
     for name, _, options in wide_type_programs.CASES:
       jobs.append((name, wide_type_programs.stencil_of(name), options))
