@@ -8,6 +8,7 @@
 // `num_bank` ways.  blockIdx.y is the tile, blockIdx.x the row in the tile.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "soda_fpga_layout.h"
 
@@ -19,14 +20,17 @@ struct Banks {
   void* ptr[4];
 };
 
-// One block per tile row (fixed in-tile coordinates in every dimension but 0):
-// the row is decoded once per block, threads walk dimension 0, four cells
-// each per trip, and the bank count is a compile-time constant — no per-cell
-// division by a run-time value.
-template <typename T, bool kPack, int kBanks>
-__global__ void __launch_bounds__(256)
-wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
-            const __grid_constant__ Banks banks) {
+// What a block works on: one tile row (fixed in-tile coordinates in every
+// dimension but 0), decoded once per block.
+struct Row {
+  bool inside;         // false: nothing of this row is moved
+  long long original;  // dense offset of in-tile coordinate i = 0
+  long long stream;    // stream offset of i = 0 (tile base + row + lag)
+  int i_lo, i_hi;      // in-tile coordinates [i_lo, i_hi) are moved
+};
+
+template <bool kPack>
+__device__ __forceinline__ Row decode_row(const soda_fpga_layout_t& a) {
   const int last = a.dim - 1;
   // this block's tile: dimension 0 of the tile index is the fastest
   int tile_index[3] = {0, 0, 0};
@@ -73,23 +77,38 @@ wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
     pitch *= a.dims[d];
     if (d < last) in_tile_pitch *= a.tile_size[d];
   }
-  if (!inside) return;
-  int i_lo = a.lo[0], i_hi = extent0 - a.hi_margin[0];
+  Row r;
+  r.inside = inside;
+  r.original = original;
+  r.i_lo = a.lo[0];
+  r.i_hi = extent0 - a.hi_margin[0];
   if (!kPack && tile_index[0] + 1 < a.tile_num[0])
-    i_hi = min(i_hi, a.lo[0] + a.tile_step[0]);   // the next tile owns the rest
-  const long long stream =
-      tile_linear * a.tile_size_linearized + row_offset + a.stream_offset;
-  T* const row_dense = dense + original;
+    r.i_hi = min(r.i_hi, a.lo[0] + a.tile_step[0]);  // the next tile owns the rest
+  r.stream = tile_linear * a.tile_size_linearized + row_offset + a.stream_offset;
+  return r;
+}
+
+// One block per tile row: threads walk dimension 0, four cells each per trip;
+// the bank count is a compile-time constant — no per-cell division by a
+// run-time value.  Element-sized accesses on both sides.
+template <typename T, bool kPack, int kBanks>
+__global__ void __launch_bounds__(256)
+wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
+            const __grid_constant__ Banks banks) {
+  const Row r = decode_row<kPack>(a);
+  if (!r.inside) return;
+  T* const row_dense = dense + r.original;
   T* bank[kBanks];
 #pragma unroll
   for (int b = 0; b < kBanks; ++b)
     bank[b] = static_cast<T*>(banks.ptr[a.bank_vec[b]]);
-  for (int i0 = i_lo + threadIdx.x * 4; i0 < i_hi; i0 += 1024) {
+  for (int i0 = r.i_lo + threadIdx.x * 4; i0 < r.i_hi; i0 += 1024) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = i0 + k;
-      if (i >= i_hi) break;
-      const unsigned long long o = static_cast<unsigned long long>(stream + i);
+      if (i >= r.i_hi) break;
+      const unsigned long long o =
+          static_cast<unsigned long long>(r.stream + i);
       T* const slot = bank[o % kBanks] + o / kBanks;
       if (kPack)
         *slot = row_dense[i];
@@ -99,15 +118,118 @@ wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
   }
 }
 
-template <typename T, bool kPack>
-void launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
-            dim3 grid, cudaStream_t s) {
-  switch (a.num_bank) {
-    case 1: wire_kernel<T, kPack, 1><<<grid, 256, 0, s>>>(a, dense, table); break;
-    case 2: wire_kernel<T, kPack, 2><<<grid, 256, 0, s>>>(a, dense, table); break;
-    case 3: wire_kernel<T, kPack, 3><<<grid, 256, 0, s>>>(a, dense, table); break;
-    default: wire_kernel<T, kPack, 4><<<grid, 256, 0, s>>>(a, dense, table); break;
+// ---- staged variant (SODA_FPGA_STAGED=1; not measured yet) -------------------
+//
+// The same row goes through shared memory so that BOTH global sides use
+// 16-byte accesses: the dense run and each bank's run are contiguous but
+// start at unrelated alignments, so each side is walked in vectors aligned to
+// ITS address (a peeled head and tail move element-wise) and the shared copy
+// is indexed element-wise in between.
+template <typename T>
+struct alignas(16) Vec16 {
+  T v[16 / sizeof(T)];
+};
+
+// Contiguous run of `n` elements between global memory `g` and `n` shared
+// elements reached through `at(j)` (j = 0..n-1), 16 bytes at a time where the
+// global address allows.  kToShared: global -> shared, else shared -> global.
+template <typename T, bool kToShared, typename At>
+__device__ __forceinline__ void move_run(T* g, int n, At at) {
+  constexpr int W = 16 / sizeof(T);
+  const int phase = static_cast<int>(
+      (reinterpret_cast<uintptr_t>(g) & 15) / sizeof(T));
+  // vector v covers run elements [v * W - phase, v * W - phase + W)
+  const int vectors = (n + phase + W - 1) / W;
+  for (int v = threadIdx.x; v < vectors; v += blockDim.x) {
+    const int first = v * W - phase;
+    if (first >= 0 && first + W <= n) {
+      Vec16<T>* const wide = reinterpret_cast<Vec16<T>*>(g + first);
+      Vec16<T> pack;
+      if (kToShared) {
+        pack = *wide;
+#pragma unroll
+        for (int k = 0; k < W; ++k) *at(first + k) = pack.v[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < W; ++k) pack.v[k] = *at(first + k);
+        *wide = pack;
+      }
+    } else {
+      for (int k = 0; k < W; ++k) {
+        const int j = first + k;
+        if (j < 0 || j >= n) continue;
+        if (kToShared)
+          *at(j) = g[j];
+        else
+          g[j] = *at(j);
+      }
+    }
   }
+}
+
+template <typename T, bool kPack, int kBanks>
+__global__ void __launch_bounds__(256)
+wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
+                   const __grid_constant__ Banks banks) {
+  extern __shared__ __align__(16) unsigned char staged_raw[];
+  T* const buf = reinterpret_cast<T*>(staged_raw);   // buf[i - i_lo]
+  const Row r = decode_row<kPack>(a);
+  if (!r.inside || r.i_hi <= r.i_lo) return;          // whole block: no barrier
+  const int n = r.i_hi - r.i_lo;
+  T* const row_dense = dense + r.original + r.i_lo;
+  if (kPack)
+    move_run<T, true>(row_dense, n, [&](int j) { return buf + j; });
+  if (!kPack) {
+    // nothing to do yet: the banks are read below
+  }
+  if (kPack) __syncthreads();
+#pragma unroll
+  for (int b = 0; b < kBanks; ++b) {
+    // cells of this row whose stream element lands in bank slot b
+    const long long first_o = r.stream + r.i_lo;
+    const int skip = static_cast<int>(((b - first_o) % kBanks + kBanks) % kBanks);
+    if (skip >= n) continue;
+    const int count = (n - skip + kBanks - 1) / kBanks;
+    T* const run = static_cast<T*>(banks.ptr[a.bank_vec[b]]) +
+                   (first_o + skip) / kBanks;
+    auto at = [&](int j) { return buf + skip + j * kBanks; };
+    if (kPack)
+      move_run<T, false>(run, count, at);
+    else
+      move_run<T, true>(run, count, at);
+  }
+  if (!kPack) {
+    __syncthreads();
+    move_run<T, false>(row_dense, n, [&](int j) { return buf + j; });
+  }
+}
+
+template <typename T, bool kPack>
+int launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
+           dim3 grid, cudaStream_t s) {
+  // staged variant: a tile row (plus nothing else) in shared memory
+  const size_t smem = static_cast<size_t>(a.tile_size[0]) * sizeof(T) + 16;
+  const char* env = getenv("SODA_FPGA_STAGED");
+  const bool staged = env != nullptr && env[0] == '1' && smem <= 200 * 1024;
+#define SODA_WIRE_LAUNCH(kBanks)                                              \
+  if (staged) {                                                               \
+    auto fn = wire_kernel_staged<T, kPack, kBanks>;                           \
+    if (smem > 48 * 1024 &&                                                   \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             static_cast<int>(smem)) != cudaSuccess)          \
+      return kLaunchFailed;                                                   \
+    fn<<<grid, 256, smem, s>>>(a, dense, table);                              \
+  } else {                                                                    \
+    wire_kernel<T, kPack, kBanks><<<grid, 256, 0, s>>>(a, dense, table);      \
+  }
+  switch (a.num_bank) {
+    case 1: SODA_WIRE_LAUNCH(1) break;
+    case 2: SODA_WIRE_LAUNCH(2) break;
+    case 3: SODA_WIRE_LAUNCH(3) break;
+    default: SODA_WIRE_LAUNCH(4) break;
+  }
+#undef SODA_WIRE_LAUNCH
+  return 0;
 }
 
 template <bool kPack>
@@ -138,13 +260,15 @@ int run(const soda_fpga_layout_t* layout, void* dense,
   // grid: x = rows of a tile (in-tile coordinates 1..), y = tiles
   dim3 grid(static_cast<unsigned>(rows), static_cast<unsigned>(tiles));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = 0;
   switch (a.elem_size) {
-    case 1: launch<uint8_t, kPack>(a, static_cast<uint8_t*>(dense), table, grid, s); break;
-    case 2: launch<uint16_t, kPack>(a, static_cast<uint16_t*>(dense), table, grid, s); break;
-    case 4: launch<uint32_t, kPack>(a, static_cast<uint32_t*>(dense), table, grid, s); break;
-    case 8: launch<uint64_t, kPack>(a, static_cast<uint64_t*>(dense), table, grid, s); break;
+    case 1: rc = launch<uint8_t, kPack>(a, static_cast<uint8_t*>(dense), table, grid, s); break;
+    case 2: rc = launch<uint16_t, kPack>(a, static_cast<uint16_t*>(dense), table, grid, s); break;
+    case 4: rc = launch<uint32_t, kPack>(a, static_cast<uint32_t*>(dense), table, grid, s); break;
+    case 8: rc = launch<uint64_t, kPack>(a, static_cast<uint64_t*>(dense), table, grid, s); break;
     default: return kBadDescriptor;
   }
+  if (rc != 0) return rc;
   return cudaGetLastError() == cudaSuccess ? 0 : kLaunchFailed;
 }
 

@@ -32,7 +32,12 @@ def main():
   for what, call in (
       ('pack', lambda: fpga_layout.pack(layout, name_in, dense, banks_in)),
       ('unpack', lambda: fpga_layout.unpack(layout, name_out, out,
-                                            banks_out))):
+                                            banks_out)),
+      ('pack staged', lambda: fpga_layout.pack(layout, name_in, dense,
+                                               banks_in)),
+      ('unpack staged', lambda: fpga_layout.unpack(layout, name_out, out,
+                                                   banks_out))):
+    os.environ['SODA_FPGA_STAGED'] = '1' if 'staged' in what else '0'
     for _ in range(3):
       call()
     torch.cuda.synchronize()
@@ -45,7 +50,7 @@ def main():
       torch.cuda.synchronize()
       times.append(start.elapsed_time(stop))
     ms = float(np.median(times))
-    print('%-6s blur %dx%d uint16 tile 2000, 2 banks: %.3f ms, %.0f GB/s '
+    print('%-13s blur %dx%d uint16 tile 2000, 2 banks: %.3f ms, %.0f GB/s '
           '(2 B read + 2 B written per cell), tiles %s' % (
               what, dims[0], dims[1], ms, cells * 4 / ms / 1e6,
               layout.tile_num), flush=True)
