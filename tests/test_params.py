@@ -128,3 +128,18 @@ def test_library_reports_params_and_checks_them():
     with pytest.raises(soda_cuda.CudaError) as info:      # no CPU fallback
       library.run([x], params={'k': np.ones((2, 1, 3), np.int16)})
     assert info.value.code == -19
+
+
+def test_entry_point_takes_the_params_after_the_outputs():
+  """`int conv3(buffer_t* in, buffer_t* out, buffer_t* w, buffer_t* bias,
+  const char* xclbin)` with C++ linkage, as reference header.py:57-60 would
+  declare it (tensors = inputs + outputs + params)."""
+  import subprocess
+  library = soda_cuda.compile_stencil(pp.stencil_of('conv3'))
+  symbols = subprocess.run(['nm', '-D', '--defined-only', library.path],
+                           stdout=subprocess.PIPE, text=True,
+                           check=True).stdout
+  assert ' T _Z5conv3P8buffer_tS0_S0_S0_PKc' in symbols
+  for name in ('soda_cuda_run_params', 'soda_cuda_set_params',
+               'soda_cuda_num_params', 'soda_cuda_param_size'):
+    assert ' T %s\n' % name in symbols
