@@ -145,3 +145,24 @@ def test_kernel_model_round_trips_both_mappings():
       layout.window_offset, layout.valid_hi_margin(), dims))))
   want[inner] = dense[inner]
   common.assert_bit_exact(back, want, 'output mapping')
+
+
+@pytest.mark.skipif(not common.have_reference(),
+                    reason='needs /root/reference')
+def test_committed_fixtures_are_what_the_reference_loops_produce():
+  """Re-runs oracle/fpga_layout_ref.py's extraction (the unmodified
+  reference's generated pack / unpack nests, compiled) on the committed
+  fixture inputs: the committed outputs must come out again."""
+  import fpga_layout_ref as ref_tool
+  name, tile, burst, dims, banks = ref_tool.FIXTURES[1]     # two banks each
+  data = np.load(os.path.join(common.GOLDEN_DIR, 'fpga_layout',
+                              '%s_%s.npz' % (name, 'x'.join(map(str, tile)))))
+  ref = ref_tool.ReferenceLayout(
+      os.path.join(common.REFERENCE_DIR, 'tests', 'src', name + '.soda'),
+      tile, burst)
+  packed = ref.pack(dims, banks, [data['in0']])
+  for b in range(4):
+    common.assert_bit_exact(packed[0][b], data['in0_bank%d' % b])
+  unpacked = ref.unpack(dims, banks,
+                        [[data['out0_bank%d' % b] for b in range(4)]])
+  common.assert_bit_exact(unpacked[0], data['out0'])
