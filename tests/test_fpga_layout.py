@@ -166,3 +166,65 @@ def test_committed_fixtures_are_what_the_reference_loops_produce():
   unpacked = ref.unpack(dims, banks,
                         [[data['out0_bank%d' % b] for b in range(4)]])
   common.assert_bit_exact(unpacked[0], data['out0'])
+
+
+def _random_layout(rng):
+  from haoda import util
+  name = rng.choice(['blur', 'sobel2d', 'denoise2d', 'heat3d', 'jacobi3d'])
+  dim = 3 if name.endswith('3d') else 2
+  tile = [int(rng.integers(8, 40)) for _ in range(dim - 1)]
+  burst = int(rng.choice([64, 128, 256, 512]))
+  stencil = core.Stencil.from_text(common.bench_text(name), tile_size=tile,
+                                   burst_width=burst, iterate=1)
+  n_banks = int(rng.integers(1, 5))            # same count on both sides
+  for stmt in list(stencil.input_stmts) + list(stencil.output_stmts):
+    stmt.dram = tuple(int(b) for b in rng.permutation(4)[:n_banks])
+  dims = tuple(int(rng.integers(12, 70)) for _ in range(dim - 1)) + (
+      int(rng.integers(6, 12)),)
+  try:
+    layout = fpga_layout.WireLayout(stencil, dims)
+    for stmt in list(stencil.input_stmts) + list(stencil.output_stmts):
+      layout.descriptor(stmt.name)
+  except util.SemanticError:
+    return None
+  if min(layout.tile_num) < 1:
+    return None
+  return stencil, layout, dims
+
+
+def test_kernel_model_equals_the_oracle_on_random_layouts():
+  """The CUDA kernel's index arithmetic (tests/wire_kernel_model.py) against
+  the numpy restatement of the reference loops, over random tile sizes,
+  burst widths, bank assignments and grids."""
+  import wire_kernel_model as model
+  rng = np.random.default_rng(2024)
+  done = 0
+  for _ in range(60):
+    made = _random_layout(rng)
+    if made is None:
+      continue
+    stencil, layout, dims = made
+    shape = tuple(reversed(dims))
+    for stmt in stencil.input_stmts:
+      width = layout.descriptor(stmt.name).elem_size
+      dtype = {2: np.uint16, 4: np.float32}[width]
+      dense = (rng.random(shape) * 60000).astype(dtype)
+      count = layout.bank_elems(stmt.name)
+      want = {b: np.full(count, 7, dtype) for b in range(4)}
+      got = {b: np.full(count, 7, dtype) for b in range(4)}
+      oracle_layout.pack(layout, stmt.name, dense, want)
+      model.run(layout.descriptor(stmt.name), dense.ravel(), got, True)
+      for b in range(4):
+        common.assert_bit_exact(got[b], want[b], '%s %s' % (stmt.name, dims))
+    for stmt in stencil.output_stmts:
+      width = layout.descriptor(stmt.name).elem_size
+      dtype = {2: np.uint16, 4: np.float32}[width]
+      count = layout.bank_elems(stmt.name)
+      banks = {b: (rng.random(count) * 60000).astype(dtype) for b in range(4)}
+      want = np.full(shape, 9, dtype)
+      got = np.full(shape, 9, dtype)
+      oracle_layout.unpack(layout, stmt.name, want, banks)
+      model.run(layout.descriptor(stmt.name), got.reshape(-1), banks, False)
+      common.assert_bit_exact(got, want, '%s %s' % (stmt.name, dims))
+    done += 1
+  assert done >= 25
