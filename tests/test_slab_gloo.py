@@ -162,3 +162,51 @@ def test_partition_and_refusals():
   if not torch.cuda.is_available():
     with pytest.raises(RuntimeError):  # no CPU fallback on the product path
       cuda_slab.SlabRunner(library, (32, 64), 0, 2)
+
+
+def test_face_decomposition_rules(monkeypatch):
+  """SlabRunner._split: minimal faces where the lead-in rows are a negligible
+  share of the slab, whole blocks of the library's decomposition where they
+  are not, and never faces that would swallow the slab."""
+  from soda import cuda_slab
+
+  class Library(FakeLibrary):
+    def chunk_rows(self, depth, dims, rows):
+      return 32
+
+    def lead_rows(self, depth):
+      return self.lead
+
+  def runner_for(name, dims, rank, world, lead):
+    library = Library(name, 2, (2,))
+    library.lead = lead
+    runner = cuda_slab.SlabRunner(library, dims, rank, world,
+                                  compute=lambda *a: None)
+    runner.on_gpu = True                 # exercise the GPU-side rule ...
+    runner._compute = runner._launch     # ... without launching anything
+    return runner
+  monkeypatch.delenv('SODA_CUDA_SLAB_FACES', raising=False)
+  # 3-D, middle rank of 4, 256 planes: 2 x 6 lead-in rows > 1 % -> blocks
+  runner = runner_for('heat3d', (64, 64, 1024), 1, 4, 6)
+  a = runner.begin - runner.local_begin
+  b = a + 256
+  assert runner._split(2, a, b) == (a + 32, b - 32, 32)
+  # the end rank has one face only
+  runner = runner_for('heat3d', (64, 64, 1024), 0, 4, 6)
+  assert runner._split(2, 0, 256) == (0, 256 - 32, 32)
+  # 2-D, 16384 rows: 2 x 18 rows are nothing -> just the reach rows
+  runner = runner_for('jacobi2d', (64, 65536), 1, 4, 18)
+  a = runner.begin - runner.local_begin
+  assert runner._split(2, a, a + 16384) == (a + 2, a + 16384 - 2, 0)
+  # the override
+  monkeypatch.setenv('SODA_CUDA_SLAB_FACES', 'chunk')
+  assert runner._split(2, a, a + 16384) == (a + 32, a + 16384 - 32, 32)
+  monkeypatch.setenv('SODA_CUDA_SLAB_FACES', 'minimal')
+  runner = runner_for('heat3d', (64, 64, 1024), 1, 4, 6)
+  a = runner.begin - runner.local_begin
+  assert runner._split(2, a, a + 256) == (a + 2, a + 256 - 2, 0)
+  # a slab of two blocks cannot give both away: minimal faces
+  monkeypatch.delenv('SODA_CUDA_SLAB_FACES')
+  runner = runner_for('heat3d', (64, 64, 256), 1, 4, 6)
+  a = runner.begin - runner.local_begin
+  assert runner._split(2, a, a + 64) == (a + 2, a + 64 - 2, 0)
