@@ -59,8 +59,12 @@ class Stage:
   """One local/output statement of one iteration."""
 
   def __init__(self, name, haoda_type, lets, expr, store_idx, is_output,
-               params=()):
+               params=(), alias=None):
     self.params = frozenset(params)   # names of param arrays
+    # replica name -> statement name: with iterate > 1 the Stencil IR calls
+    # output k of the first iteration `<input k>_iter1` (reference
+    # core.py:347-351), also where a later statement reads it
+    self.alias = dict(alias or {})
     self.name = name
     self.haoda_type = haoda_type
     self.c_type = util.get_c_type(haoda_type)
@@ -77,7 +81,7 @@ class Stage:
       # a param is a small constant array indexed absolutely (the golden
       # loop reads `<name>_img[i][j]`, reference host.py:1095-1097)
       return Load(ref.name, tuple(ref.idx))
-    return Load(ref.name,
+    return Load(self.alias.get(ref.name, ref.name),
                 tuple(a - b for a, b in zip(ref.idx, self.store_idx)))
 
   def _note_load(self, obj, _):
@@ -254,10 +258,14 @@ def extract_program(stencil):
   # the first replica of every statement; with iterate > 1 the reference
   # names an output of iteration 0 ``<input>_iter1`` — undo that by position
   replicas = list(stencil.tensors.values())[n_in:n_in + len(stage_names)]
+  alias = {}
+  if stencil.iterate > 1:
+    alias = {in_name + '_iter1': out_name for in_name, out_name in
+             zip(stencil.input_names, output_names)}
   by_name = {
       name: Stage(name, tensor.haoda_type, tensor.lets, tensor.expr,
                   tensor.st_ref.idx, name in output_names,
-                  params=stencil.param_names)
+                  params=stencil.param_names, alias=alias)
       for name, tensor in zip(stage_names, replicas)}
   known = set(stencil.input_names) | set(stencil.param_names)
   placed, order, pending = set(known), [], list(stage_names)

@@ -64,3 +64,26 @@ def dims_of(stencil, seed):
   if stencil.dim == 2:
     return (rng.choice((1024, 1061, 2048)), rng.randint(90, 200))
   return (rng.choice((128, 131, 256)), rng.randint(35, 64), rng.randint(30, 48))
+
+
+# Hand-written programs for shapes the random generator does not produce:
+# two inputs and two outputs, the second output reading the first within the
+# iteration (under iterate > 1 the Stencil IR calls that read `a_iter1`).
+EXTRA = {
+    'chain2': ('kernel: chain2\nburst width: 64\nunroll factor: 1\n'
+               'input float: a(32, *)\ninput float: b(32, *)\n'
+               'output float: o0(0, 0) = a(0, 0) * 0.5f + b(1, 0) * 0.25f\n'
+               'output float: o1(0, 0) = a(0, 1) * 0.125f + o0(-1, 0) * 0.5f - '
+               'b(0, 0) * 0.25f\niterate: 3\n', (1024, 150)),
+    'chain3d': ('kernel: chain3d\nburst width: 64\nunroll factor: 1\n'
+                'input float: a(16, 8, *)\ninput float: b(16, 8, *)\n'
+                'local float: m(0, 0, 0) = a(0, 1, 0) + b(0, 0, -1)\n'
+                'output float: o0(0, 0, 0) = m(0, -1, 0) * 0.5f + a(1, 0, 0) * '
+                '0.25f\n'
+                'output float: o1(0, 0, 0) = o0(0, 0, 1) * 0.5f + m(0, 0, 0) * '
+                '0.25f + b(0, 0, 0) * 0.125f\niterate: 2\n', (128, 40, 36)),
+}
+
+
+def extra_stencil(name):
+  return core.Stencil.from_text(EXTRA[name][0])

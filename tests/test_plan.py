@@ -190,6 +190,32 @@ def test_random_programs_schedule_correctly_in_registers(generated):
   reg_sim.check_outputs(sched, dims, outs)
 
 
+@pytest.mark.parametrize('name', ['chain2', 'chain3d'])
+def test_output_read_by_a_later_statement(name, monkeypatch):
+  """Under iterate > 1 the Stencil IR renames output k of the first
+  iteration `<input k>_iter1` (reference core.py:347-351), also inside the
+  statements that read it; the program extraction must undo that."""
+  import random_programs as rp
+  import reg_schedule_sim as reg_sim
+  monkeypatch.setenv('SODA_CUDA_TUNED', '0')
+  stencil = rp.extra_stencil(name)
+  program = plan.extract_program(stencil)
+  readers = [s for s in program.stages if s.name == 'o1']
+  assert any(load.parent == 'o0' for load in readers[0].loads)
+  dims = (300, 31) if program.dim == 2 else (140, 40, 13)
+  schedules = list(codegen.make_schedules(program))
+  try:      # all iterations in one launch too, where that fits
+    schedules.append(codegen.make_schedule(program, program.iterate,
+                                           codegen.Options()))
+  except Exception:   # pylint: disable=broad-except
+    pass
+  assert schedules
+  for sched in schedules:
+    runner = reg_sim if sched.style == 'reg' else sim
+    outs = runner.run_schedule(sched, dims, 9)
+    runner.check_outputs(sched, dims, outs)
+
+
 def test_window_without_store_point_is_rejected():
   text = ('kernel: k\nburst width: 64\nunroll factor: 1\niterate: 1\n'
           'input float: a(8, *)\nlocal float: l(0, 0) = a(0, -1)\n'

@@ -39,3 +39,18 @@ def test_random_program_matches_oracle(seed):
     # compare by class (see common.assert_bit_exact)
     common.assert_bit_exact(g, w, 'seed %d:\n%s' % (
         seed, rp.program_text(seed)), any_nan=True)
+
+
+@pytest.mark.parametrize('name', sorted(rp.EXTRA))
+def test_outputs_read_by_later_statements(name):
+  stencil = rp.extra_stencil(name)
+  dims = rp.EXTRA[name][1]
+  orc = golden.Oracle(stencil)
+  library = soda_cuda.compile_stencil(stencil)
+  for seed in (1, 2):
+    inputs = common.random_inputs(orc, dims, seed=seed)
+    want = orc.run(inputs)
+    got = library.run(inputs)
+    assert len(got) == 2
+    for k, (g, w) in enumerate(zip(got, want)):
+      common.assert_bit_exact(g, w, '%s output %d' % (name, k))

@@ -74,6 +74,8 @@ def main():
     import random_programs
     for seed in random_programs.SEEDS:
       jobs.append(('rnd%d' % seed, random_programs.stencil_of(seed), {}))
+    for name in random_programs.EXTRA:
+      jobs.append((name, random_programs.extra_stencil(name), {}))
     import wide_type_programs
     for name, _, options in wide_type_programs.CASES:
       jobs.append((name, wide_type_programs.stencil_of(name), options))
