@@ -190,6 +190,65 @@ def test_random_programs_schedule_correctly_in_registers(generated):
   reg_sim.check_outputs(sched, dims, outs)
 
 
+@st.composite
+def multi_io_program(draw):
+  """One or two inputs and as many outputs (later outputs may read earlier
+  ones), up to two locals, 1-3 iterations."""
+  dim = draw(st.integers(2, 3))
+  n_io = draw(st.integers(1, 2))
+  n_local = draw(st.integers(0, 2))
+  inputs = ['a', 'b'][:n_io]
+  names = list(inputs)
+  lines = ['kernel: rnd', 'burst width: 64', 'unroll factor: 1']
+  for name in inputs:
+    lines.append('input float: %s(%s*)' % (
+        name, ''.join('8, ' for _ in range(dim - 1))))
+  zero = ', '.join('0' for _ in range(dim))
+  targets = ['l%d' % k for k in range(n_local)] + [
+      'o%d' % k for k in range(n_io)]
+  for k, target in enumerate(targets):
+    terms = []
+    for _ in range(draw(st.integers(1, 3))):
+      parent = draw(st.sampled_from(names))
+      off = [draw(st.integers(-2, 2)) for _ in range(dim)]
+      terms.append('%s(%s)' % (parent, ', '.join(map(str, off))))
+    # every window must contain the store point (Program.check_windows)
+    terms += ['%s(%s)' % (name, zero) for name in [names[-1]] + inputs]
+    lines.append('%s float: %s(%s) = %s' % (
+        'local' if k < n_local else 'output', target, zero,
+        ' + '.join(terms)))
+    names.append(target)
+  iterate = draw(st.integers(1, 3))
+  lines.append('iterate: %d' % iterate)
+  return '\n'.join(lines) + '\n', dim, iterate
+
+
+@settings(max_examples=20, deadline=None)
+@given(multi_io_program())
+def test_random_multi_output_programs_schedule_correctly(generated):
+  import os
+  import reg_schedule_sim as reg_sim
+  text, dim, iterate = generated
+  program = plan.extract_program(core.Stencil.from_text(text))
+  program.check_windows()
+  dims = (300, 29) if dim == 2 else (140, 40, 13)
+  before = os.environ.get('SODA_CUDA_TUNED')
+  os.environ['SODA_CUDA_TUNED'] = '0'
+  try:
+    sched = codegen.make_schedule(program, iterate, codegen.Options())
+  except Exception as e:   # pylint: disable=broad-except
+    assert any(word in str(e) for word in ('halo', 'shared memory')), str(e)
+    return
+  finally:
+    if before is None:
+      del os.environ['SODA_CUDA_TUNED']
+    else:
+      os.environ['SODA_CUDA_TUNED'] = before
+  runner = reg_sim if sched.style == 'reg' else sim
+  outs = runner.run_schedule(sched, dims, 9)
+  runner.check_outputs(sched, dims, outs)
+
+
 @pytest.mark.parametrize('name', ['chain2', 'chain3d'])
 def test_output_read_by_a_later_statement(name, monkeypatch):
   """Under iterate > 1 the Stencil IR renames output k of the first
