@@ -126,3 +126,36 @@ def test_partial_iterations_and_border():
   common.assert_bit_exact(three, direct, 'iterate override')
   assert not three[:3].any() and not three[:, :3].any()
   assert three[3:-3, 3:-3].all()
+
+
+@pytest.mark.skipif(not common.have_reference(),
+                    reason='needs /root/reference')
+@pytest.mark.parametrize('name', ['chain2', 'chain3d'])
+def test_reference_harness_accepts_the_oracle_on_chained_outputs(name,
+                                                                 tmp_path):
+  """Two outputs, the second reading the first, iterated (the Stencil IR's
+  `<input>_iter1` alias): the unmodified reference's generated harness judges
+  the oracle's outputs — ramp and random inputs — and notices one wrong
+  cell."""
+  import random_programs as rp
+  import ref_harness
+  soda_file = tmp_path / (name + '.soda')
+  soda_file.write_text(rp.EXTRA[name][0])
+  stencil = golden.stencil_from_file(str(soda_file))
+  harness = ref_harness.RefHarness(
+      ref_harness.build_ref(str(soda_file), None, force=True), stencil)
+  orc = golden.Oracle(stencil)
+  dims = (60, 40) if stencil.dim == 2 else (24, 20, 18)
+  assert harness.test(dims, orc.run) == 0
+
+  def on_random_inputs(inputs):
+    for array, fresh in zip(inputs, common.random_inputs(orc, dims, seed=5)):
+      array[...] = fresh
+    return orc.run(inputs)
+  assert harness.test(dims, on_random_inputs) == 0
+
+  def one_wrong_cell(inputs):
+    outputs = orc.run(inputs)
+    outputs[1][tuple(n // 2 for n in outputs[1].shape)] += 1
+    return outputs
+  assert harness.test(dims, one_wrong_cell) == 1
