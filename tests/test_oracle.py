@@ -159,3 +159,30 @@ def test_reference_harness_accepts_the_oracle_on_chained_outputs(name,
     outputs[1][tuple(n // 2 for n in outputs[1].shape)] += 1
     return outputs
   assert harness.test(dims, one_wrong_cell) == 1
+
+
+@pytest.mark.skipif(not common.have_reference(),
+                    reason='needs /root/reference')
+@pytest.mark.parametrize('seed', [0, 1, 5, 7, 13])
+def test_reference_harness_accepts_the_oracle_on_random_programs(seed,
+                                                                 tmp_path):
+  """Beyond the benchmarks: seeded random programs (integer and float types,
+  a stage of another width, 2-D / 3-D, up to 4 iterations) — the unmodified
+  reference parses them, generates its golden harness, and that harness
+  accepts the oracle's outputs (integers compare exactly, host.py:1118-1146)."""
+  import random_programs as rp
+  import ref_harness
+  soda_file = tmp_path / ('rnd%d.soda' % seed)
+  soda_file.write_text(rp.program_text(seed))
+  stencil = golden.stencil_from_file(str(soda_file))
+  harness = ref_harness.RefHarness(
+      ref_harness.build_ref(str(soda_file), None, force=True), stencil)
+  orc = golden.Oracle(stencil)
+  dims = (60, 40) if stencil.dim == 2 else (24, 20, 18)
+  assert harness.test(dims, orc.run) == 0
+
+  def on_random_inputs(inputs):
+    for array, fresh in zip(inputs, common.random_inputs(orc, dims, seed=5)):
+      array[...] = fresh
+    return orc.run(inputs)
+  assert harness.test(dims, on_random_inputs) == 0
