@@ -185,3 +185,27 @@ def test_visit_does_not_modify_the_receiver():
   expr.visit(lambda obj, _: ir.make_var('z') if isinstance(obj, ir.Ref)
              else obj)
   assert str(expr) == before
+
+
+@pytest.mark.skipif(not common.have_reference(),
+                    reason='needs /root/reference')
+def test_same_stages_as_reference_on_random_programs(tmp_path):
+  """The committed golden file covers the benchmarks; here the unmodified
+  reference frontend (oracle/ref_tool.py describe, in its own process) and
+  this one describe seeded random programs — stage order, store indices,
+  golden-loop bounds, lowered C expressions — identically."""
+  import json
+  import subprocess
+  import sys
+  import random_programs as rp
+  texts = [rp.program_text(seed) for seed in (0, 3, 5, 7, 10)] + [
+      text for text, _ in rp.EXTRA.values()]
+  for k, text in enumerate(texts):
+    path = tmp_path / ('p%d.soda' % k)
+    path.write_text(text)
+    done = subprocess.run(
+        [sys.executable, os.path.join(common.ROOT, 'oracle', 'ref_tool.py'),
+         'describe', str(path)], stdout=subprocess.PIPE,
+        stderr=subprocess.PIPE, text=True, check=True)
+    assert describe(core.Stencil.from_text(text)) == json.loads(done.stdout), \
+        text
