@@ -116,7 +116,7 @@ def _render(stage, ref_code, k):
       obj.name = 'let_' + obj.name
     return obj
   lets = ['const %s let_%s = %s;' % (
-      let.c_type, let.name, plan_mod.strip_parens(let.expr.visit(swap).c_expr))
+      let.c_type, let.name, let.expr.visit(swap).c_expr)
           for let in stage.lets]
   return lets, stage.expr.visit(swap).c_expr
 

@@ -102,17 +102,13 @@ class Stage:
       if _is_ref(obj):
         return Code(ref_code(self.load_of(obj)))
       return obj
+    # like the golden loop (host.py:1111-1114) the right-hand side keeps its
+    # parentheses: the IR's `unparenthesize` is not bracket-matching and would
+    # turn `(a == b) & (c)` into `a == b) & (c`
     lets = ['const %s %s = %s;' % (let.c_type, let.name,
-                                   strip_parens(let.expr.visit(swap).c_expr))
+                                   let.expr.visit(swap).c_expr)
             for let in self.lets]
     return lets, self.expr.visit(swap).c_expr
-
-
-def strip_parens(text):
-  # ``Let.c_expr`` unparenthesizes its right-hand side (ir Let.c_expr)
-  while text[:1] == '(' and text[-1:] == ')':
-    text = text[1:-1]
-  return text
 
 
 class Program:

@@ -160,3 +160,35 @@ def test_random_programs_emit_code_nvcc_accepts(tmp_path, monkeypatch):
     dims = (40, 30) if stencil.dim == 2 else (24, 20, 18)
     out = orc.run(common.random_inputs(orc, dims, seed=seed))
     assert out[0].shape == tuple(reversed(dims))
+
+
+def test_let_right_hand_sides_keep_their_parentheses(tmp_path, monkeypatch):
+  """The IR's `unparenthesize` is not bracket-matching (reference
+  src/haoda/ir/__init__.py:877-881): applied to a let it turns
+  `(a == b) & (c)` into `a == b) & (c`.  The golden loop does not apply it
+  (host.py:1111-1114); neither may the kernels.  Seeds whose oracle compiles
+  must give kernels nvcc accepts."""
+  import subprocess
+  import golden
+  import expression_programs as ep
+  from soda import cuda as soda_cuda
+  monkeypatch.setenv('SODA_CUDA_TUNED', '0')
+  text = ('kernel: lets\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+          'input int16: a(8, *)\n'
+          'output int16: v = (a(0, 0) == a(1, 0)) & (a(0, 1) == 3) '
+          'o(0, 0) = a(0, 0) + v\n')
+  _, kernel, _ = soda_cuda.generate_sources(core.Stencil.from_text(text))
+  assert ') & (' in kernel and '== 3);' in kernel
+  for seed in (3, 55):          # found by the random search: lets with `&`
+    stencil = core.Stencil.from_text(ep.program(seed))
+    golden.build(stencil, build_dir=str(tmp_path))
+    _, kernel, _ = soda_cuda.generate_sources(stencil)
+    path = tmp_path / ('k%d.cu' % seed)
+    path.write_text(kernel)
+    done = subprocess.run(
+        ['nvcc'] + soda_cuda.ARCH_FLAGS + [
+            '-std=c++17', '-fmad=false', '-I', soda_cuda.CSRC_DIR, '-I',
+            soda_cuda.INCLUDE_DIR, '-c', str(path), '-o',
+            str(tmp_path / 'k.o')],
+        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert done.returncode == 0, ep.program(seed) + done.stdout[-1500:]
