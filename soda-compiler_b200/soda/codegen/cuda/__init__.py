@@ -175,8 +175,19 @@ def _make_reg_schedule(program, depth, options, limit):
     prefetch = options.prefetch if options.prefetch is not None else (
         (9 if paired else 6) * (groups - 2))
     while True:
-      sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
-                                   paired=paired, groups=groups)
+      try:
+        sched = plan_mod.RegSchedule(program, depth, vec, warps, (), prefetch,
+                                     paired=paired, groups=groups)
+      except util.SemanticError as e:
+        # pairing chosen by default but impossible for this chain (outputs
+        # produced at different delays): the unpaired register kernel, not
+        # the shared-memory family
+        if not paired or options.paired or 'cannot pair' not in str(e):
+          raise
+        paired = False
+        if options.prefetch is None:
+          prefetch = 6 * (groups - 2)
+        continue
       # keep three blocks per SM resident: shorter boxes if the queues of all
       # inputs do not fit (programs with several inputs or long periods)
       if (options.prefetch is not None or sched.flat_box <= sched.period or
