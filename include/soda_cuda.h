@@ -84,9 +84,16 @@ int soda_cuda_num_outputs(void);
 const char* soda_cuda_tensor_name(int kind, int index);
 const char* soda_cuda_tensor_type(int kind, int index);
 int soda_cuda_tensor_elem_size(int kind, int index);
-/* Offsets of the inputs read by one output cell after `iterate` iterations:
- * lo[d] <= offset <= hi[d]; outputs are defined on [-lo, dims - hi). */
+/* Offsets of the inputs read by the cells of ANY output after `iterate`
+ * iterations: lo[d] <= offset <= hi[d] (the union over the outputs: what a
+ * caller needs to size halos and ghost planes). */
 int soda_cuda_window(int iterate, int32_t lo[4], int32_t hi[4]);
+/* The same box for output number `output` alone: that output is defined on
+ * [-lo, dims - hi) — the loop bounds of the reference's golden loop for that
+ * tensor (window from all inputs to it, reference
+ * src/soda/codegen/xilinx/host.py:1082-1091, src/soda/core.py:793-835).
+ * Outputs of one program may have different windows. */
+int soda_cuda_window_of(int output, int iterate, int32_t lo[4], int32_t hi[4]);
 
 /* ---- running ---------------------------------------------------------------
  * soda_cuda_run: the generic form of `<app>()` — n_in input and n_out output
@@ -121,8 +128,10 @@ int soda_cuda_run_device(const void* const* inputs, void* const* outputs,
 
 /* One kernel launch: `depth` fused iterations (must be a compiled depth, see
  * soda_cuda_depths) producing streamed planes [row_begin, row_end) of the
- * outputs from the full input arrays; cells outside [valid_lo, valid_hi) are
- * stored as 0.  For slab-partitioned multi-GPU runs (soda/cuda.py). */
+ * outputs from the full input arrays.  `valid_lo` / `valid_hi` hold one box of
+ * 4 ints per output (output k: valid_lo[4k .. 4k+3]); cells of output k
+ * outside its box are stored as 0.  For slab-partitioned multi-GPU runs
+ * (soda/cuda_slab.py). */
 int soda_cuda_launch(int depth, const void* const* inputs,
                      void* const* outputs, const int32_t* dims, int row_begin,
                      int row_end, const int32_t* valid_lo,

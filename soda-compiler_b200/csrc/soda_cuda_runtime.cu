@@ -162,17 +162,40 @@ CUtensorMapDataType tma_type(int elem) {
   }
 }
 
+// One box of kRtMaxDim ints per output.
+struct Boxes {
+  int32_t lo[kRtMaxTensors * kRtMaxDim];
+  int32_t hi[kRtMaxTensors * kRtMaxDim];
+};
+
+// Where each output is defined after `iterate` iterations: the bounds of the
+// reference's golden loop for that tensor (host.py:1082-1091).
 void valid_region(const ProgramDesc& prog, int iterate, const int32_t* dims,
-                  int32_t* lo, int32_t* hi) {
-  const int* w = prog.window + iterate * 2 * kRtMaxDim;
-  for (int d = 0; d < kRtMaxDim; ++d) {
-    lo[d] = 0;
-    hi[d] = 1;
+                  Boxes* boxes) {
+  for (int k = 0; k < kRtMaxTensors; ++k) {
+    int32_t* lo = boxes->lo + k * kRtMaxDim;
+    int32_t* hi = boxes->hi + k * kRtMaxDim;
+    for (int d = 0; d < kRtMaxDim; ++d) {
+      lo[d] = 0;
+      hi[d] = 1;
+    }
+    if (k >= prog.n_out) continue;
+    const int* w =
+        prog.out_window + (iterate * prog.n_out + k) * 2 * kRtMaxDim;
+    for (int d = 0; d < prog.dim; ++d) {
+      lo[d] = std::max(0, -w[d]);
+      hi[d] = dims[d] - std::max(0, w[kRtMaxDim + d]);
+    }
   }
-  for (int d = 0; d < prog.dim; ++d) {
-    lo[d] = std::max(0, -w[d]);
-    hi[d] = dims[d] - std::max(0, w[kRtMaxDim + d]);
-  }
+}
+
+// Intermediate launches store every cell they own.
+void full_region(const ProgramDesc& prog, const int32_t* dims, Boxes* boxes) {
+  for (int k = 0; k < kRtMaxTensors; ++k)
+    for (int d = 0; d < kRtMaxDim; ++d) {
+      boxes->lo[k * kRtMaxDim + d] = 0;
+      boxes->hi[k * kRtMaxDim + d] = d < prog.dim ? dims[d] : 1;
+    }
 }
 
 // Blocks along the streamed dimension: minimise (waves x steps per block).
@@ -321,10 +344,13 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
     args.dims[d] = d < prog.dim ? dims[d] : 1;
     args.stride[d] = stride;
     stride *= args.dims[d];
-    args.valid_lo[d] = d < prog.dim ? valid_lo[d] : 0;
-    args.valid_hi[d] = d < prog.dim ? valid_hi[d] : 1;
     args.tiles[d] = 1;
   }
+  for (int k = 0; k < prog.n_out; ++k)
+    for (int d = 0; d < kRtMaxDim; ++d) {
+      args.valid_lo[k][d] = d < prog.dim ? valid_lo[k * kRtMaxDim + d] : 0;
+      args.valid_hi[k][d] = d < prog.dim ? valid_hi[k * kRtMaxDim + d] : 1;
+    }
   cells = stride;
   if (cells >= (1LL << 40)) return kBufferExtentsTooLarge;
   long long tile_blocks = 1;
@@ -456,11 +482,9 @@ int run_device(const ProgramDesc& prog, const void* const* inputs,
       if (scratch[k] == nullptr) return kDeviceMallocFailed;
     }
   }
-  int32_t full_lo[kRtMaxDim] = {0, 0, 0, 0};
-  int32_t full_hi[kRtMaxDim] = {1, 1, 1, 1};
-  for (int d = 0; d < prog.dim; ++d) full_hi[d] = dims[d];
-  int32_t fin_lo[kRtMaxDim], fin_hi[kRtMaxDim];
-  valid_region(prog, iterate, dims, fin_lo, fin_hi);
+  Boxes full, fin;
+  full_region(prog, dims, &full);
+  valid_region(prog, iterate, dims, &fin);
 
   {
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -480,7 +504,7 @@ int run_device(const ProgramDesc& prog, const void* const* inputs,
     for (int k = 0; k < prog.n_out; ++k)
       dst[k] = to_outputs ? outputs[k] : scratch[k];
     rc = launch(prog, depths[l], src, dst, dims, 0, dims[prog.dim - 1],
-                last ? fin_lo : full_lo, last ? fin_hi : full_hi, stream);
+                last ? fin.lo : full.lo, last ? fin.hi : full.hi, stream);
     if (rc != kSuccess) return rc;
     for (int k = 0; k < prog.n_out; ++k) src[k] = dst[k];
   }
@@ -579,11 +603,9 @@ int run_pipelined(const ProgramDesc& prog, buffer_t* const* inputs,
   }
   for (int j = 0; j < n_launch; ++j)
     hold[j] = std::max(reach_hi[j], j > 0 ? reach_lo[j - 1] : 0);
-  int32_t full_lo[kRtMaxDim] = {0, 0, 0, 0};
-  int32_t full_hi[kRtMaxDim] = {1, 1, 1, 1};
-  for (int d = 0; d < prog.dim; ++d) full_hi[d] = dims[d];
-  int32_t fin_lo[kRtMaxDim], fin_hi[kRtMaxDim];
-  valid_region(prog, prog.iterate, dims, fin_lo, fin_hi);
+  Boxes full, fin;
+  full_region(prog, dims, &full);
+  valid_region(prog, prog.iterate, dims, &fin);
 
   std::vector<int> frontier(n_launch, 0);
   std::vector<cudaEvent_t> events;
@@ -633,7 +655,7 @@ int run_pipelined(const ProgramDesc& prog, buffer_t* const* inputs,
         dst[k] = to_outputs ? out_dev[k] : scratch[k];
       if (target > frontier[j]) {
         rc = launch(prog, depths[j], src, dst, dims, frontier[j], target,
-                    last ? fin_lo : full_lo, last ? fin_hi : full_hi, s_run);
+                    last ? fin.lo : full.lo, last ? fin.hi : full.hi, s_run);
         if (rc != kSuccess) return rc;
         frontier[j] = target;
       }

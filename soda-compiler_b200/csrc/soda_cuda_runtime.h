@@ -60,6 +60,11 @@ struct ProgramDesc {
   // side 1: max offset) of the inputs read by outputs after n iterations,
   // n = 0..iterate.  Defines the valid region [-min, dims - max).
   const int* window;
+  // out_window[((n * n_out + k) * 2 + side) * kRtMaxDim + d]: the same box for
+  // output k alone.  Every output is defined on [-min, dims - max) of ITS OWN
+  // window (the reference bounds each tensor's golden loop separately,
+  // host.py:1082-1091); `window` above is the union and sizes halos.
+  const int* out_window;
   // STENCIL_DIM_d of the reference host (host.py:1188-1189): window extents.
   int stencil_dim[kRtMaxDim];
   int n_variants;
@@ -111,8 +116,9 @@ int run_device(const ProgramDesc& prog, const void* const* inputs,
                cudaStream_t stream);
 
 // One launch of the variant with `depth` fused iterations producing streamed
-// planes [row_begin, row_end) of the outputs; cells outside
-// [valid_lo, valid_hi) are stored as 0.  Building block for slab-partitioned
+// planes [row_begin, row_end) of the outputs; cells of output k outside
+// [valid_lo[4k..], valid_hi[4k..]) are stored as 0 (one box of kRtMaxDim ints
+// per output).  Building block for slab-partitioned
 // multi-GPU runs, where the caller owns ping-pong buffers and halo exchange.
 int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
            void* const* outputs, const int32_t* dims, int row_begin,

@@ -123,7 +123,28 @@ class Options:
         self.min_blocks, self.groups)
 
 
+# Whitelisted by the grammar (reference src/soda/grammar.py:25-32) but not
+# callable from a SODA expression: their C prototypes take a pointer or a
+# string, which the DSL has no way to write (the reference's generated code
+# does not compile for them either).
+UNCALLABLE = {'frexp': 'an `int*` exponent', 'modf': 'a `double*` integral '
+              'part', 'remquo': 'an `int*` quotient', 'nan': 'a string'}
+
+
+def _check_calls(program):
+  def visit(obj, _):
+    if type(obj).__name__ == 'Call' and obj.name in UNCALLABLE:
+      raise util.SemanticError(
+          '`%s` needs %s argument, which a SODA expression cannot supply' %
+          (obj.name, UNCALLABLE[obj.name]))
+    return obj
+  for stage in program.stages:
+    for node in tuple(let.expr for let in stage.lets) + (stage.expr,):
+      node.visit(visit)
+
+
 def check_supported(program):
+  _check_calls(program)
   for name, haoda_type in list(program.types.items()):
     if haoda_type not in SUPPORTED_TYPES:
       raise util.SemanticError(
@@ -327,7 +348,10 @@ def make_schedules(program, options=None):
     for depth in (2, 4, 8, 16):
       if depth > iterate:
         break
-      sched = make_schedule(program, depth, options)
+      try:
+        sched = make_schedule(program, depth, options)
+      except util.SemanticError:
+        break     # this depth fits no kernel family: keep the last that did
       if sched.style != 'reg' or history_registers(sched) > REG_HISTORY_BUDGET:
         break
       main = depth

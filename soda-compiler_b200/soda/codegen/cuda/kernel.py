@@ -150,7 +150,10 @@ def emit_kernel(p, sched):
             'valid region (else 0)')
   p.println('int pos[%d];' % VPT)
   p.println('long long goff[%d];' % VPT)
-  p.println('unsigned own[%d], val[%d];' % (VPT, VPT))
+  p.println('unsigned own[%d];' % VPT)
+  for n in range(len(sched.outputs)):
+    p.println('unsigned val%d[%d];   // output %d: cells in ITS valid region' %
+              (n, VPT, n))
   p.println('int gx[%d];' % VPT)
   for d in range(1, s):
     p.println('int gc%d[%d];' % (d, VPT))
@@ -168,17 +171,22 @@ def emit_kernel(p, sched):
   p.println('(void)rest;')
   p.println('gx[j] = org0 + c0;')
   p.println('long long off = gx[j];')
-  p.println('bool mine = true, ok = true;')
+  p.println('bool mine = true;')
+  for n in range(len(sched.outputs)):
+    p.println('bool ok%d = true;' % n)
   for d in range(1, s):
     p.println('gc%d[j] = org%d + c%d;' % (d, d, d))
     p.println('off += gc%d[j] * a.stride[%d];' % (d, d))
     p.println('mine = mine && c%d >= %d && c%d < %d && gc%d[j] < a.dims[%d];' %
               (d, sched.tile_halo_lo[d], d,
                sched.tile[d] - sched.tile_halo_hi[d], d, d))
-    p.println('ok = ok && gc%d[j] >= a.valid_lo[%d] && gc%d[j] < '
-              'a.valid_hi[%d];' % (d, d, d, d))
+    for n in range(len(sched.outputs)):
+      p.println('ok%d = ok%d && gc%d[j] >= a.valid_lo[%d][%d] && gc%d[j] < '
+                'a.valid_hi[%d][%d];' % (n, n, d, n, d, d, n, d))
   p.println('goff[j] = off;')
-  p.println('unsigned m = 0, v = 0;')
+  p.println('unsigned m = 0;')
+  for n in range(len(sched.outputs)):
+    p.println('unsigned v%d = 0;' % n)
   p.println('#pragma unroll')
   p.println('for (int k = 0; k < %d; ++k)' % V)
   p.do_scope()
@@ -186,10 +194,13 @@ def emit_kernel(p, sched):
   p.println('if (mine && c0 + k >= %d && c0 + k < %d && x < a.dims[0]) '
             'm |= 1u << k;' % (sched.tile_halo_lo[0],
                                sched.tile[0] - sched.tile_halo_hi[0]))
-  p.println('if (ok && x >= a.valid_lo[0] && x < a.valid_hi[0]) v |= 1u << k;')
+  for n in range(len(sched.outputs)):
+    p.println('if (ok%d && x >= a.valid_lo[%d][0] && x < a.valid_hi[%d][0]) '
+              'v%d |= 1u << k;' % (n, n, n, n))
   p.un_scope()
   p.println('own[j] = m;')
-  p.println('val[j] = v;')
+  for n in range(len(sched.outputs)):
+    p.println('val%d[j] = v%d;' % (n, n))
   p.un_scope()
   p.println()
 
@@ -307,8 +318,9 @@ def _emit_stage(p, sched, lay, node):
   if node.output_index is not None:
     p.println('const int row = base + i - %d;' % node.delay)
     p.println('const bool row_mine = row >= r0 && row < r1;')
-    p.println('const bool row_ok = row >= a.valid_lo[%d] && row < '
-              'a.valid_hi[%d];' % (s, s))
+    p.println('const bool row_ok = row >= a.valid_lo[%d][%d] && row < '
+              'a.valid_hi[%d][%d];' % (node.output_index, s,
+                                       node.output_index, s))
   p.println('#pragma unroll')
   p.println('for (int j = 0; j < %d; ++j)' % VPT)
   p.do_scope()
@@ -375,7 +387,7 @@ def _emit_stage(p, sched, lay, node):
     p.println('%s* const dst = static_cast<%s*>(a.out_ptr[%d]) + row * '
               'a.stride[%d] + goff[j];' % (node.c_type, node.c_type,
                                            node.output_index, s))
-    p.println('const unsigned keep = row_ok ? val[j] : 0u;')
+    p.println('const unsigned keep = row_ok ? val%d[j] : 0u;' % node.output_index)
     p.println('if (keep != %du)' % full)
     p.do_scope()
     p.println('#pragma unroll')

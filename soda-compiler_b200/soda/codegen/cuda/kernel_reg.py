@@ -292,9 +292,12 @@ class _Emitter:
     p.println('// owns (store) and cells in the valid region (else 0)')
     p.println('int pos[%d];' % VPT)
     p.println('long long goff[%d];' % VPT)
-    p.println('unsigned own[%d], val[%d];' % (VPT, VPT))
-    p.println('bool fast[%d];   // whole vector owned and valid: one 128-bit '
-              'store' % VPT)
+    p.println('unsigned own[%d];' % VPT)
+    for n in range(len(sched.outputs)):
+      p.println('unsigned val%d[%d];   // output %d: cells in ITS valid region'
+                % (n, VPT, n))
+      p.println('bool fast%d[%d];   // whole vector owned and valid: one '
+                '128-bit store' % (n, VPT))
     p.println('bool xin[%d];   // the vector lies inside the grid in the tiled '
               'dims' % VPT)
     p.println('int gx[%d];' % VPT)
@@ -317,20 +320,25 @@ class _Emitter:
     p.println('(void)rest;')
     p.println('gx[j] = org0 + c0;')
     p.println('long long off = gx[j];')
-    p.println('bool mine = true, ok = true, inside = true;')
+    p.println('bool mine = true, inside = true;')
+    for n in range(len(sched.outputs)):
+      p.println('bool ok%d = true;' % n)
     for d in range(1, s):
       p.println('gc%d[j] = org%d + c%d;' % (d, d, d))
       p.println('off += gc%d[j] * a.stride[%d];' % (d, d))
       p.println('mine = mine && c%d >= %d && c%d < %d && gc%d[j] < a.dims[%d];'
                 % (d, sched.tile_halo_lo[d], d,
                    sched.tile[d] - sched.tile_halo_hi[d], d, d))
-      p.println('ok = ok && gc%d[j] >= a.valid_lo[%d] && gc%d[j] < '
-                'a.valid_hi[%d];' % (d, d, d, d))
+      for n in range(len(sched.outputs)):
+        p.println('ok%d = ok%d && gc%d[j] >= a.valid_lo[%d][%d] && gc%d[j] < '
+                  'a.valid_hi[%d][%d];' % (n, n, d, n, d, d, n, d))
       p.println('inside = inside && gc%d[j] >= 0 && gc%d[j] < a.dims[%d];' % (
           d, d, d))
     p.println('goff[j] = off;')
     p.println('xin[j] = inside && gx[j] >= 0 && gx[j] + %d <= a.dims[0];' % V)
-    p.println('unsigned m = 0, v = 0;')
+    p.println('unsigned m = 0;')
+    for n in range(len(sched.outputs)):
+      p.println('unsigned v%d = 0;' % n)
     p.println('#pragma unroll')
     p.println('for (int k = 0; k < %d; ++k)' % V)
     p.do_scope()
@@ -338,12 +346,15 @@ class _Emitter:
     p.println('if (mine && c0 + k >= %d && c0 + k < %d && x < a.dims[0]) '
               'm |= 1u << k;' % (sched.tile_halo_lo[0],
                                  sched.tile[0] - sched.tile_halo_hi[0]))
-    p.println('if (ok && x >= a.valid_lo[0] && x < a.valid_hi[0]) v |= 1u << k;')
+    for n in range(len(sched.outputs)):
+      p.println('if (ok%d && x >= a.valid_lo[%d][0] && x < a.valid_hi[%d][0]) '
+                'v%d |= 1u << k;' % (n, n, n, n))
     p.un_scope()
     p.println('own[j] = m;')
-    p.println('val[j] = v;')
-    p.println('fast[j] = m == %du && v == %du && a.vec_store;' % (
-        (1 << V) - 1, (1 << V) - 1))
+    for n in range(len(sched.outputs)):
+      p.println('val%d[j] = v%d;' % (n, n))
+      p.println('fast%d[j] = m == %du && v%d == %du && a.vec_store;' % (
+          n, (1 << V) - 1, n, (1 << V) - 1))
     p.un_scope()
     p.println()
 
@@ -360,11 +371,11 @@ class _Emitter:
       n, lag = node.output_index, self.out_lag(node)
       p.println('const int mine_lo%d = %d, mine_hi%d = (r1 - r0) + %d;' % (
           n, sched.lead + lag, n, sched.lead + lag))
-      p.println('const int ok_lo%d = max(mine_lo%d, a.valid_lo[%d] - base + '
-                '%d);' % (n, n, s, lag))
+      p.println('const int ok_lo%d = max(mine_lo%d, a.valid_lo[%d][%d] - base '
+                '+ %d);' % (n, n, n, s, lag))
       p.println('const unsigned ok_n%d = static_cast<unsigned>(max(0, min('
-                'mine_hi%d, a.valid_hi[%d] - base + %d) - ok_lo%d));' % (
-                    n, n, s, lag, n))
+                'mine_hi%d, a.valid_hi[%d][%d] - base + %d) - ok_lo%d));' % (
+                    n, n, n, s, lag, n))
       p.println('%s* op%d[%d];   // row of step 0 (dereferenced only inside '
                 'the window)' % (node.c_type, n, self.VPT))
       p.println('#pragma unroll')
@@ -779,7 +790,7 @@ class _Emitter:
     if node.output_index is not None:
       n = node.output_index
       half = '.v.y' if sched.paired else ''
-      p.println('if (row_ok && fast[j])')
+      p.println('if (row_ok && fast%d[j])' % n)
       p.do_scope()
       p.println('%s o[%d];' % (node.c_type, V))
       p.println('#pragma unroll')
@@ -792,7 +803,7 @@ class _Emitter:
       p.do_scope()
       p.println('// tile or grid edge: cells outside the valid region are '
                 'stored as 0')
-      p.println('const unsigned keep = row_ok ? val[j] : 0u;')
+      p.println('const unsigned keep = row_ok ? val%d[j] : 0u;' % n)
       p.println('%s o[%d];' % (node.c_type, V))
       p.println('#pragma unroll')
       p.println('for (int k = 0; k < %d; ++k)' % V)

@@ -190,9 +190,10 @@ class Program:
     return history
 
   def window(self, iterations=None):
-    """``(lo, hi)`` per dimension: bounding box of every offset at which the
-    outputs of ``iterations`` chained iterations read the original inputs —
-    the box of the reference's overall stencil window (core.py:793-830)."""
+    """``(lo, hi)`` per dimension: bounding box of every offset at which ANY
+    output of ``iterations`` chained iterations reads the original inputs.
+    This union sizes halos, tiles and ghost planes; which cells of an output
+    are *defined* is a per-output matter, see ``window_of``."""
     iterations = self.iterate if iterations is None else iterations
     zero = (0,) * self.dim
     if iterations == 0:
@@ -203,6 +204,20 @@ class Program:
       return zero, zero
     return (tuple(min(o[0][d] for o in outs) for d in range(self.dim)),
             tuple(max(o[1][d] for o in outs) for d in range(self.dim)))
+
+  def window_of(self, output, iterations=None):
+    """``(lo, hi)`` per dimension: bounding box of the offsets at which output
+    number ``output`` (or the output of that name) reads the original inputs
+    after ``iterations`` chained iterations — the box of the reference's
+    overall stencil window from all inputs to THAT tensor
+    (core.py:793-830), which is what bounds its golden loop nest
+    (host.py:1082-1091).  Outputs of one program may differ."""
+    iterations = self.iterate if iterations is None else iterations
+    zero = (0,) * self.dim
+    if iterations == 0:
+      return zero, zero
+    name = output if isinstance(output, str) else self.output_names[output]
+    return self._reach(iterations)[-1][name] or (zero, zero)
 
   def check_windows(self):
     """Every stage's window must contain its own store point in every
@@ -222,11 +237,17 @@ class Program:
                 'point in dimension %d: the window must include 0' %
                 (stage.name, box[0][d], box[1][d], d))
 
-  def valid_region(self, dims, iterations=None):
-    """``[(lo, hi)]`` per dimension where outputs are defined: the bounds of
-    the reference's golden loop (host.py:1082-1091)."""
-    lo, hi = self.window(iterations)
+  def valid_region(self, dims, iterations=None, output=0):
+    """``[(lo, hi)]`` per dimension where output ``output`` is defined: the
+    bounds of the reference's golden loop for that tensor
+    (host.py:1082-1091)."""
+    lo, hi = self.window_of(output, iterations)
     return [(max(0, -l), d - max(0, h)) for l, h, d in zip(lo, hi, dims)]
+
+  def valid_regions(self, dims, iterations=None):
+    """``valid_region`` of every output, in program order."""
+    return [self.valid_region(dims, iterations, k)
+            for k in range(len(self.outputs))]
 
 
 def emit_param_pointers(p, program):

@@ -169,6 +169,7 @@ class Library:
         ('soda_cuda_tensor_type', c_char_p, [c_int, c_int]),
         ('soda_cuda_tensor_elem_size', c_int, [c_int, c_int]),
         ('soda_cuda_window', c_int, [c_int, i32p, i32p]),
+        ('soda_cuda_window_of', c_int, [c_int, c_int, i32p, i32p]),
         ('soda_cuda_run', c_int, [bufpp, bufpp, c_char_p]),
         ('soda_cuda_run_params', c_int, [bufpp, bufpp, bufpp, c_char_p]),
         ('soda_cuda_num_params', c_int, []),
@@ -220,7 +221,8 @@ class Library:
                           tuple(size[:rank])))
 
   def window(self, iterate=None):
-    """``(lo, hi)`` offsets per dim read by an output cell after ``iterate``."""
+    """``(lo, hi)`` offsets per dim read by the cells of any output after
+    ``iterate`` iterations (the union over the outputs: sizes halos)."""
     lo, hi = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 4)()
     code = self._lib.soda_cuda_window(
         self.iterate if iterate is None else iterate, lo, hi)
@@ -228,9 +230,24 @@ class Library:
       raise CudaError('soda_cuda_window', code)
     return tuple(lo[:self.dim]), tuple(hi[:self.dim])
 
-  def valid_region(self, dims, iterate=None):
-    lo, hi = self.window(iterate)
+  def window_of(self, output, iterate=None):
+    """The window of output number ``output`` alone: bounds where THAT output
+    is defined (reference host.py:1082-1091)."""
+    lo, hi = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 4)()
+    code = self._lib.soda_cuda_window_of(
+        output, self.iterate if iterate is None else iterate, lo, hi)
+    if code:
+      raise CudaError('soda_cuda_window_of', code)
+    return tuple(lo[:self.dim]), tuple(hi[:self.dim])
+
+  def valid_region(self, dims, iterate=None, output=0):
+    """``[(lo, hi)]`` per dimension where output ``output`` is defined."""
+    lo, hi = self.window_of(output, iterate)
     return [(max(0, -l), n - max(0, h)) for l, h, n in zip(lo, hi, dims)]
+
+  def valid_regions(self, dims, iterate=None):
+    return [self.valid_region(dims, iterate, k)
+            for k in range(len(self.outputs))]
 
   @property
   def stats(self):
@@ -421,12 +438,25 @@ class Library:
 
   def launch(self, depth, inputs, outputs, dims, row_begin, row_end,
              valid_lo, valid_hi, stream=None, chunk_rows=0):
-    """Enqueue one kernel launch (see soda_cuda_launch[_chunked])."""
+    """Enqueue one kernel launch (see soda_cuda_launch[_chunked]).
+
+    ``valid_lo`` / ``valid_hi``: one box per output (a list of per-dimension
+    lists), or a single box that applies to every output."""
     pad = lambda xs, fill: (ctypes.c_int32 * 4)(
         *(list(xs) + [fill] * (4 - len(xs))))
+
+    def boxes(box, fill):
+      per_output = (list(box) if box and hasattr(box[0], '__len__')
+                    else [box] * len(self.outputs))
+      if len(per_output) != len(self.outputs):
+        raise ValueError('one valid box per output')
+      flat = []
+      for one in per_output:
+        flat += list(one) + [fill] * (4 - len(one))
+      return (ctypes.c_int32 * len(flat))(*flat)
     code = self._lib.soda_cuda_launch_chunked(
         depth, self._pointers(inputs), self._pointers(outputs), pad(dims, 1),
-        row_begin, row_end, pad(valid_lo, 0), pad(valid_hi, 1),
+        row_begin, row_end, boxes(valid_lo, 0), boxes(valid_hi, 1),
         chunk_rows or 0, stream)
     if code:
       raise CudaError('soda_cuda_launch(%s)' % self.app_name, code)

@@ -67,7 +67,8 @@ class SlabRunner:
     device: torch device of the local arrays (default: current CUDA device).
     compute: test hook replacing the kernel launch,
       ``compute(depth, inputs, outputs, local_dims, row_begin, row_end,
-      valid_lo, valid_hi)``; the product path always launches the CUDA kernel
+      valid_lo, valid_hi)`` (one box per output); the product path always
+      launches the CUDA kernel
       and refuses to run without a GPU.
   """
 
@@ -344,22 +345,34 @@ class SlabRunner:
       left -= fits[0]
     return depths
 
-  def valid_region(self, iterate):
-    """``[(lo, hi)]`` per dimension of the global grid after ``iterate``
-    iterations.  More iterations than the program was compiled for means
-    repeated application with the fed-back tensors (``u <- output``; the
-    reference refuses to iterate programs whose inputs and outputs differ,
-    src/soda/core.py:228-233, so its harness would be called once per
-    application): every application shrinks the region by its own window,
-    exactly as the golden loop bounds do (host.py:1082-1091)."""
+  def valid_regions(self, iterate):
+    """Per output, ``[(lo, hi)]`` per dimension of the global grid after
+    ``iterate`` iterations: each output is defined on the box of its own
+    window (reference host.py:1082-1091).  More iterations than the program
+    was compiled for means repeated application with the fed-back tensors
+    (``u <- output``; the reference refuses to iterate programs whose inputs
+    and outputs differ, src/soda/core.py:228-233, so its harness would be
+    called once per application): an application reads arrays that are
+    defined where every output of the previous one is, and shrinks that box
+    by each output's own window, as the golden loop bounds do."""
+    n_out = len(self.library.outputs)
     if iterate <= self.library.iterate:
-      return self.library.valid_region(self.global_dims, iterate)
-    lo, hi = [0] * self.dim, [0] * self.dim
+      return self.library.valid_regions(self.global_dims, iterate)
+    common_lo, common_hi = [0] * self.dim, [0] * self.dim
+    margins = []
     for depth in self.plan(iterate):
-      step_lo, step_hi = self.library.window(depth)
-      lo = [a + max(0, -b) for a, b in zip(lo, step_lo)]
-      hi = [a + max(0, b) for a, b in zip(hi, step_hi)]
-    return [(l, max(l, n - h)) for l, h, n in zip(lo, hi, self.global_dims)]
+      margins = []
+      for k in range(n_out):
+        step_lo, step_hi = self.library.window_of(k, depth)
+        margins.append(([a + max(0, -b) for a, b in zip(common_lo, step_lo)],
+                        [a + max(0, b) for a, b in zip(common_hi, step_hi)]))
+      common_lo = [max(m[0][d] for m in margins) for d in range(self.dim)]
+      common_hi = [max(m[1][d] for m in margins) for d in range(self.dim)]
+    return [[(l, max(l, n - h)) for l, h, n in zip(lo, hi, self.global_dims)]
+            for lo, hi in margins]
+
+  def valid_region(self, iterate, output=0):
+    return self.valid_regions(iterate)[output]
 
   def launches_per_run(self, iterate):
     faces = (1 if self.rank > 0 else 0) + (1 if self.rank + 1 < self.world
@@ -372,12 +385,17 @@ class SlabRunner:
     depths = self.plan(iterate)
     if len(depths) > 1 and not self.feedback:
       raise ValueError('iterations need outputs that feed the inputs')
-    region = self.valid_region(iterate)
-    full_lo, full_hi = [0] * self.dim, list(self.local_dims)
-    fin_lo = [lo for lo, _ in region]
-    fin_hi = [hi for _, hi in region]
-    fin_lo[-1] = min(max(0, fin_lo[-1] - self.local_begin), self.local_rows)
-    fin_hi[-1] = min(max(0, fin_hi[-1] - self.local_begin), self.local_rows)
+    n_out = len(self.library.outputs)
+    full_lo = [[0] * self.dim for _ in range(n_out)]
+    full_hi = [list(self.local_dims) for _ in range(n_out)]
+    fin_lo, fin_hi = [], []      # one box per output, in local coordinates
+    for region in self.valid_regions(iterate):
+      lo = [a for a, _ in region]
+      hi = [b for _, b in region]
+      lo[-1] = min(max(0, lo[-1] - self.local_begin), self.local_rows)
+      hi[-1] = min(max(0, hi[-1] - self.local_begin), self.local_rows)
+      fin_lo.append(lo)
+      fin_hi.append(hi)
     a = self.begin - self.local_begin
     b = a + (self.end - self.begin)
     current = list(self.inputs)

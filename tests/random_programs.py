@@ -87,3 +87,66 @@ EXTRA = {
 
 def extra_stencil(name):
   return core.Stencil.from_text(EXTRA[name][0])
+
+
+# --- programs with several outputs --------------------------------------------
+# The outputs of one program are defined on different boxes (the reference
+# bounds each tensor's golden loop by the window from all inputs to THAT
+# tensor, host.py:1082-1091): one-sided reads, an output that reads an earlier
+# output of the same iteration, locals shared by some outputs only.
+MULTI_SEEDS = tuple(range(100, 160))
+
+
+def multi_program_text(seed):
+  rng = random.Random(seed)
+  dim = rng.choice((2, 2, 3))
+  n_out = rng.choice((2, 2, 3))
+  # iterate > 1 needs as many inputs as outputs (reference core.py:228-243)
+  n_in = n_out if rng.random() < 0.6 else rng.randint(1, 2)
+  n_local = rng.randint(0, 2)
+  inputs = ['i%d' % k for k in range(n_in)]
+  lines = ['kernel: multi%d' % seed, 'burst width: 64', 'unroll factor: 1']
+  for name in inputs:
+    lines.append('input float: %s(%s*)' % (
+        name, ''.join('8, ' for _ in range(dim - 1))))
+  zero = ', '.join('0' for _ in range(dim))
+  names = list(inputs)
+  # the reference's dataflow graph needs every input and local consumed
+  unread = list(inputs)
+  for k in range(n_local + n_out):
+    is_local = k < n_local
+    target = 'l%d' % k if is_local else 'o%d' % (k - n_local)
+    sign = rng.choice((-1, 1, 0))     # one-sided windows are the common case
+    terms = []
+    last = k + 1 == n_local + n_out
+    parents = [rng.choice(names) for _ in range(rng.randint(1, 3))]
+    parents += unread if last else unread[:1]
+    for parent in parents:
+      if parent in unread:
+        unread.remove(parent)
+      off = [rng.randint(min(0, 2 * sign) if sign else -2,
+                         max(0, 2 * sign) if sign else 2) for _ in range(dim)]
+      terms.append('%s(%s) * %s' % (parent, ', '.join(map(str, off)),
+                                    rng.choice(('0.5f', '0.25f', '0.125f'))))
+    # every window must contain the store point (Program.check_windows): a
+    # read of an input at the store point itself
+    terms.append('%s(%s) * 0.0625f' % (rng.choice(inputs), zero))
+    lines.append('%s float: %s(%s) = %s' % (
+        'local' if is_local else 'output', target, zero, ' + '.join(terms)))
+    names.append(target)
+    if is_local:
+      unread.append(target)
+  iterate = rng.randint(1, 3) if n_in == n_out else 1
+  lines.append('iterate: %d' % iterate)
+  return '\n'.join(lines) + '\n'
+
+
+def multi_stencil(seed):
+  return core.Stencil.from_text(multi_program_text(seed))
+
+
+def multi_dims(stencil, seed):
+  rng = random.Random(2000 + seed)
+  if stencil.dim == 2:
+    return (rng.choice((300, 333, 512)), rng.randint(60, 120))
+  return (rng.choice((64, 67, 128)), rng.randint(24, 40), rng.randint(20, 30))

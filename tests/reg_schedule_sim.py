@@ -51,7 +51,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
   n_nodes = len(sched.nodes)
   outs = [np.full(dims[::-1], UNWRITTEN, dtype=np.int64)
           for _ in sched.outputs]
-  valid = sched.program.valid_region(dims, sched.depth)
+  valids = sched.program.valid_regions(dims, sched.depth)
   n_tiles = [-(-dims[d] // sched.own[d]) for d in range(s)]
   n_chunks = -(-dims[s] // chunk_rows)
   guard = sched.guard_elems
@@ -193,6 +193,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
             if r0 <= out_row < r1:
               inside = np.ones(plane, dtype=bool)
               if final:
+                valid = valids[node.output_index]
                 inside &= valid[s][0] <= out_row < valid[s][1]
                 for d in range(s):
                   inside &= (gcoord[d] >= valid[d][0]) & (
@@ -215,14 +216,14 @@ def run_schedule(sched, dims, chunk_rows, final=True):
 
 def check_outputs(sched, dims, outs, final=True):
   dims = tuple(dims)
-  valid = sched.program.valid_region(dims, sched.depth)
+  valids = sched.program.valid_regions(dims, sched.depth)
   grids = np.meshgrid(*[np.arange(n) for n in dims[::-1]], indexing='ij')
   coords = grids[::-1]
-  inside = np.ones(dims[::-1], dtype=bool)
-  for c, (lo, hi) in zip(coords, valid):
-    inside &= (c >= lo) & (c < hi)
   lanes = 2 if sched.paired else 1
-  for node, out in zip(sched.outputs, outs):
+  for node, out, valid in zip(sched.outputs, outs, valids):
+    inside = np.ones(dims[::-1], dtype=bool)
+    for c, (lo, hi) in zip(coords, valid):
+      inside &= (c >= lo) & (c < hi)
     assert (out != UNWRITTEN).all(), 'unwritten cells'
     want = _code(node.index + (lanes - 1) * len(sched.nodes), coords, dims)
     assert (out[inside] == want[inside]).all(), 'wrong cells in valid region'

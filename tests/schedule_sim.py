@@ -33,7 +33,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
   tile = sched.tile
   plane = sched.plane_elems
   outs = [np.full(dims[::-1], -7, dtype=np.int64) for _ in sched.outputs]
-  valid = sched.program.valid_region(dims, sched.depth)
+  valids = sched.program.valid_regions(dims, sched.depth)
   n_tiles = [-(-dims[d] // sched.own[d]) for d in range(s)]
   n_chunks = -(-dims[s] // chunk_rows)
   guard = sched.guard_elems
@@ -116,6 +116,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
             store = owned.copy()
             inside = np.ones(plane, dtype=bool)
             if final:
+              valid = valids[node.output_index]
               inside &= valid[s][0] <= row < valid[s][1]
               for d in range(s):
                 inside &= (gcoord[d] >= valid[d][0]) & (gcoord[d] < valid[d][1])
@@ -131,13 +132,13 @@ def check_outputs(sched, dims, outs, final=True):
   """Every cell of the valid region holds the right identity; with ``final``
   every other cell holds 0; nothing is left unwritten."""
   dims = tuple(dims)
-  valid = sched.program.valid_region(dims, sched.depth)
+  valids = sched.program.valid_regions(dims, sched.depth)
   grids = np.meshgrid(*[np.arange(n) for n in dims[::-1]], indexing='ij')
   coords = grids[::-1]
-  inside = np.ones(dims[::-1], dtype=bool)
-  for c, (lo, hi) in zip(coords, valid):
-    inside &= (c >= lo) & (c < hi)
-  for node, out in zip(sched.outputs, outs):
+  for node, out, valid in zip(sched.outputs, outs, valids):
+    inside = np.ones(dims[::-1], dtype=bool)
+    for c, (lo, hi) in zip(coords, valid):
+      inside &= (c >= lo) & (c < hi)
     assert (out != -7).all(), 'unwritten cells'
     want = _code(node, coords, dims)
     assert (out[inside] == want[inside]).all(), 'wrong cells in valid region'

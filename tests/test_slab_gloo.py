@@ -39,8 +39,15 @@ class FakeLibrary:
   def window(self, iterate=None):
     return self.program.window(self.iterate if iterate is None else iterate)
 
-  def valid_region(self, dims, iterate=None):
-    return self.program.valid_region(dims, iterate)
+  def window_of(self, output, iterate=None):
+    return self.program.window_of(
+        output, self.iterate if iterate is None else iterate)
+
+  def valid_region(self, dims, iterate=None, output=0):
+    return self.program.valid_region(dims, iterate, output)
+
+  def valid_regions(self, dims, iterate=None):
+    return self.program.valid_regions(dims, iterate)
 
 
 def _oracle_compute(name):
@@ -50,10 +57,10 @@ def _oracle_compute(name):
     results = orc.run([t.numpy() for t in inputs])
     grids = np.meshgrid(*[np.arange(n) for n in reversed(local_dims)],
                         indexing='ij')[::-1]
-    inside = np.ones(tuple(reversed(local_dims)), dtype=bool)
-    for coord, lo, hi in zip(grids, valid_lo, valid_hi):
-      inside &= (coord >= lo) & (coord < hi)
-    for out, result in zip(outputs, results):
+    for k, (out, result) in enumerate(zip(outputs, results)):
+      inside = np.ones(tuple(reversed(local_dims)), dtype=bool)
+      for coord, lo, hi in zip(grids, valid_lo[k], valid_hi[k]):
+        inside &= (coord >= lo) & (coord < hi)
       masked = np.where(inside, result, 0).astype(result.dtype)
       out[row_begin:row_end] = torch.from_numpy(masked[row_begin:row_end])
   return compute

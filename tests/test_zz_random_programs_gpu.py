@@ -54,3 +54,31 @@ def test_outputs_read_by_later_statements(name):
     assert len(got) == 2
     for k, (g, w) in enumerate(zip(got, want)):
       common.assert_bit_exact(g, w, '%s output %d' % (name, k))
+
+
+# every 3rd seed: 20 programs whose outputs are defined on different boxes
+MULTI_GPU_SEEDS = rp.MULTI_SEEDS[::3]
+
+
+@pytest.mark.parametrize('seed', MULTI_GPU_SEEDS)
+def test_multi_output_program_matches_oracle(seed):
+  """Each output is zeroed outside ITS OWN valid box (reference
+  host.py:1082-1091) and equals the golden loop inside it — whole arrays, bit
+  for bit; host buffers (pipelined or not) and one-launch device runs."""
+  stencil = rp.multi_stencil(seed)
+  orc = golden.Oracle(stencil)
+  library = soda_cuda.compile_stencil(stencil)
+  dims = rp.multi_dims(stencil, seed)
+  inputs = common.random_inputs(orc, dims, seed=seed)
+  want = orc.run(inputs)
+  got = library.run(inputs)
+  regions = library.valid_regions(dims)
+  assert len(got) == len(want) == len(regions)
+  for k, (g, w) in enumerate(zip(got, want)):
+    common.assert_bit_exact(g, w, 'seed %d output %d:\n%s' % (
+        seed, k, rp.multi_program_text(seed)), any_nan=True)
+    # the oracle's border is 0 exactly outside the reference's box
+    box = tuple(slice(lo, hi) for lo, hi in reversed(regions[k]))
+    outside = np.ones(w.shape, dtype=bool)
+    outside[box] = False
+    assert not w[outside].any() and not g[outside].any()

@@ -76,6 +76,11 @@ def main():
       jobs.append(('rnd%d' % seed, random_programs.stencil_of(seed), {}))
     for name in random_programs.EXTRA:
       jobs.append((name, random_programs.extra_stencil(name), {}))
+    import test_zz_random_programs_gpu as zz
+    for seed in zz.MULTI_GPU_SEEDS:
+      jobs.append(('multi%d' % seed, random_programs.multi_stencil(seed), {}))
+    import test_math_calls
+    jobs.append(('calls', core.Stencil.from_text(test_math_calls.TEXT), {}))
     import wide_type_programs
     for name, _, options in wide_type_programs.CASES:
       jobs.append((name, wide_type_programs.stencil_of(name), options))
