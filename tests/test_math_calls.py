@@ -10,7 +10,9 @@ through the CUDA backend.
   need pointer / string arguments no SODA expression can supply and raise
   SemanticError instead of an nvcc error.
 * GPU: the program below — only exactly specified functions (correctly
-  rounded or exact in IEEE-754 / C99) — equals the CPU oracle bit for bit.
+  rounded or exact in IEEE-754 / C99; `pow` is not: CUDA's differed from
+  glibc's by 1 ulp in 2 of 9933 cells, capture r2a) — equals the CPU oracle
+  bit for bit.
 """
 import subprocess
 
@@ -31,7 +33,7 @@ unroll factor: 1
 iterate: 1
 input int32: a(32, *)
 input float: f(32, *)
-output double: o0(0, 0) = sqrt(a(0, 0)) + ldexp(f(0, 0), a(1, 0)) + scalbn(f(0, 1), 3) + scalbln(f(1, 0), a(0, 1)) + fabs(a(0, 0)) + pow(a(1, 1), 2)
+output double: o0(0, 0) = sqrt(a(0, 0)) + ldexp(f(0, 0), a(1, 0)) + scalbn(f(0, 1), 3) + scalbln(f(1, 0), a(0, 1)) + fabs(a(0, 0))
 output int32: o1(0, 0) = ilogb(f(0, 0)) + lround(f(1, 0)) + lrint(f(0, 1)) + llround(f(1, 1)) + llrint(f(0, 0)) + ilogb(a(0, 0))
 output double: o2(0, 0) = nexttoward(f(0, 0), f(1, 0)) + fmod(f(0, 0), f(0, 1)) + floor(f(0, 0)) + ceil(f(1, 0)) + trunc(f(0, 1)) + round(f(1, 1)) + rint(f(0, 0)) + nearbyint(f(1, 0)) + remainder(f(0, 0), f(1, 1)) + copysign(f(0, 0), a(0, 0)) + nextafter(f(0, 0), f(0, 1)) + fdim(f(0, 0), f(1, 0)) + fmax(f(0, 0), a(1, 0)) + fmin(f(0, 1), f(1, 1)) + fma(f(0, 0), f(1, 0), f(0, 1))
 '''
