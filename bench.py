@@ -15,10 +15,21 @@ computed: weak scaling, value = all ranks' cell updates / s.
 What is timed
   value     inputs resident in HBM, CUDA events around K steps on the launch
             stream, max over ranks.
-  e2e       the same K steps through the reference-facing C ABI entry
+  e2e       the same workload through the reference-facing C ABI entry
             (soda_cuda_run, the generic form of `<app>(buffer_t*...)`) with
             pinned HOST buffers: H2D of the input and D2H of the output are
-            inside the timed region.
+            inside the timed region.  With N > 1 it is ONE call on the global
+            16384 x (16384 N) grid with "devices=0,..,N-1": the runtime cuts
+            the host arrays into one slab per device (rank 0 makes the call,
+            the other ranks wait).  `copy_ceiling` is the same bytes moved by
+            plain cudaMemcpyAsync in both directions at once with no compute:
+            what this machine's host<->device path allows at N devices.
+  extra     BASELINE configs 3, 4 and 5, device-resident, outside
+            ms_per_step: sobel2d / denoise2d 32768^2 (N = 1), heat3d /
+            jacobi3d 1024^3 x 32 and denoise3d 768^3 x 16 applications cut
+            into N slabs (STRONG scaling), each with its recomputed roofline
+            fraction; with N > 1 also a small sharded run compared bit for
+            bit with the same run on one GPU.
   roofline  the streaming kernel: algorithmic bytes per launch (8 B x cells:
             each input cell read once, each output cell written once;
             SURVEY.md 8d) / mean launch time, against the measured HBM copy
@@ -179,7 +190,7 @@ def run_reference(args, rank):
       'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
       'data': 'synthetic (reference initialiser, host.py:1033-1051)',
-      'config': workload_config(1),
+      'config': workload_config(args.gpus),
       'cpu_baseline': {'value': value, 'unit': 'GCell/s', 'cores': cores,
                        'kind': 'port', 'sample': sample},
       'e2e': {'value': value, 'unit': 'GCell/s', 'h2d_bytes_per_step': 0,
@@ -200,6 +211,174 @@ def workload_config(n_gpus):
           'l2': 'inputs (1.07 GB per GPU) exceed the 126 MB L2; no flush'}
 
 
+# BASELINE configs 3, 4, 5: (program, iterate, global dims, bytes per cell
+# update at T = 1, runs at N > 1)
+EXTRA_CASES = (
+    ('sobel2d', 1, (32768, 32768), 4, False),
+    ('denoise2d', 1, (32768, 32768), 12, False),
+    ('heat3d', 32, (1024, 1024, 1024), 8, True),
+    ('jacobi3d', 32, (1024, 1024, 1024), 8, True),
+    ('denoise3d', 16, (768, 768, 768), 12, True),
+)
+
+
+def extra_stencil(name, iterate):
+  """The program compiled for `iterate` iterations, or for one when the
+  reference refuses to iterate it (denoise: inputs != outputs, reference
+  core.py:228-233) — then it is applied `iterate` times with u <- output."""
+  from soda import core
+  path = os.path.join(ROOT, 'benchmarks', name + '.soda')
+  try:
+    return core.Stencil.from_file(path, iterate=iterate)
+  except Exception:   # pylint: disable=broad-except
+    return core.Stencil.from_file(path, iterate=1)
+
+
+def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
+  """Configs 3-5, device-resident, CUDA events, max over ranks; the global
+  grid is fixed and cut into `world` slabs (strong scaling)."""
+  import numpy as np
+  import torch
+  from soda import cuda as soda_cuda, cuda_slab
+  results = []
+  for name, iterate, dims, bytes_per_cell, sharded in EXTRA_CASES:
+    if world > 1 and not sharded:
+      continue
+    entry = {'workload': '%s.soda %s iterate %d' % (
+        name, 'x'.join(map(str, dims)), iterate), 'n_gpus': world,
+             'scaling': 'strong' if world > 1 else 'single GPU'}
+    try:
+      library = soda_cuda.compile_stencil(extra_stencil(name, iterate))
+      feedback = None
+      if len(library.inputs) != len(library.outputs):
+        feedback = {1: 0}        # denoise: u <- output, f stays
+        entry['host_level_applications'] = iterate
+      runner = cuda_slab.SlabRunner(library, dims, rank, world,
+                                    feedback=feedback)
+      owned = []
+      generator = torch.Generator(device='cuda').manual_seed(1 + rank)
+      for local_in in runner.inputs:
+        shape = runner.owned(local_in).shape
+        if local_in.dtype.is_floating_point:
+          owned.append(torch.rand(shape, device='cuda', generator=generator)
+                       .to(local_in.dtype))
+        else:
+          owned.append(torch.randint(0, 30000, shape, device='cuda',
+                                     generator=generator).to(local_in.dtype))
+      runner.load_local(owned)
+      del owned
+      for _ in range(2):
+        runner.run(iterate)
+      times = []
+      for _ in range(reps):
+        barrier()
+        start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
+        start.record()
+        runner.run(iterate)
+        stop.record()
+        torch.cuda.synchronize()
+        times.append(max_over_ranks(start.elapsed_time(stop)))
+      ms = float(np.median(times))
+      cells = float(np.prod(dims))
+      passes = len(runner.plan(iterate))
+      achieved = cells * bytes_per_cell * passes / (ms * 1e6)   # GB/s, all GPUs
+      entry.update({
+          'ms': ms, 'value': cells * iterate / (ms * 1e6), 'unit': 'GCell/s',
+          'temporal_depth': runner.plan(iterate)[0], 'passes': passes,
+          'launches_rank0': runner.launches_per_run(iterate),
+          'roofline': {
+              'bound': 'hbm', 'achieved': achieved, 'peak': peak * world,
+              'unit': 'GB/s', 'frac': achieved / (peak * world),
+              'algorithmic_bytes_per_pass': cells * bytes_per_cell,
+              'traffic': None,
+              'traffic_source': 'not measured in this run; ncu captures of '
+                                'these kernels are under profiles/'}})
+      del runner
+      library.release()
+      torch.cuda.empty_cache()
+    except Exception as e:   # pylint: disable=broad-except
+      entry['error'] = '%s: %s' % (type(e).__name__, str(e)[:300])
+    results.append(entry)
+  return results
+
+
+def sharded_parity(rank, world, barrier):
+  """N > 1: a small heat3d run cut into `world` slabs (halo exchange per
+  launch, soda/cuda_slab.py) against the SAME run on one GPU (rank 0, whole
+  grid), bit for bit — SURVEY.md 8e "result invariance"."""
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  from soda import cuda as soda_cuda, cuda_slab
+  name, iterate, dims = 'heat3d', 6, (256, 128, 32 * world)
+  library = soda_cuda.compile_stencil(extra_stencil(name, 32))
+  shape = tuple(reversed(dims))
+  full = torch.rand(shape, device='cuda',
+                    generator=torch.Generator(device='cuda').manual_seed(7))
+  runner = cuda_slab.SlabRunner(library, dims, rank, world)
+  runner.load_local([full[runner.begin:runner.end].clone()])
+  mine = runner.run(iterate)[0].contiguous()
+  torch.cuda.synchronize()
+  rows = [e - b for b, e in cuda_slab.partition(dims[-1], world)]
+  if rank == 0:
+    whole = torch.empty(shape, dtype=torch.float32, device='cuda')
+    library.run_device([full], [whole], dims, iterate,
+                       torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+  parts = [torch.empty((r,) + shape[1:], dtype=torch.float32, device='cuda')
+           for r in rows] if rank == 0 else None
+  # gather the slabs on rank 0 (NCCL send/recv; sizes differ by at most one)
+  if rank == 0:
+    parts[0].copy_(mine)
+    for src in range(1, world):
+      dist.recv(parts[src], src=src)
+  else:
+    dist.send(mine, dst=0)
+  barrier()
+  del runner
+  if rank != 0:
+    return None
+  sharded = torch.cat(parts)
+  same = bool(torch.equal(sharded.view(torch.int32), whole.view(torch.int32)))
+  return {'case': '%s %s x%d, %d slabs vs one GPU' % (
+      name, 'x'.join(map(str, dims)), iterate, world),
+          'bit_identical': same,
+          'cells_differing': int((sharded.view(torch.int32) !=
+                                  whole.view(torch.int32)).sum().item())}
+
+
+def copy_ceiling(world, slab_bytes, reps=3):
+  """ms to move `slab_bytes` to each of `world` devices and as many back, both
+  directions at once, with plain cudaMemcpyAsync from pinned memory and no
+  compute: what the host<->device path of this machine allows."""
+  import torch
+  host_in, host_out, dev, streams = [], [], [], []
+  for d in range(world):
+    with torch.cuda.device(d):
+      host_in.append(torch.empty(slab_bytes, dtype=torch.uint8,
+                                 pin_memory=True))
+      host_out.append(torch.empty(slab_bytes, dtype=torch.uint8,
+                                  pin_memory=True))
+      dev.append((torch.empty(slab_bytes, dtype=torch.uint8, device='cuda'),
+                  torch.empty(slab_bytes, dtype=torch.uint8, device='cuda')))
+      streams.append((torch.cuda.Stream(), torch.cuda.Stream()))
+  times = []
+  for _ in range(reps + 1):
+    for d in range(world):
+      torch.cuda.synchronize(d)
+    t0 = time.perf_counter()
+    for d in range(world):
+      with torch.cuda.device(d):
+        with torch.cuda.stream(streams[d][0]):
+          dev[d][0].copy_(host_in[d], non_blocking=True)
+        with torch.cuda.stream(streams[d][1]):
+          host_out[d].copy_(dev[d][1], non_blocking=True)
+    for d in range(world):
+      torch.cuda.synchronize(d)
+    times.append((time.perf_counter() - t0) * 1e3)
+  return sorted(times[1:])[len(times[1:]) // 2]
+
+
 def main():
   parser = argparse.ArgumentParser()
   parser.add_argument('--gpus', type=int, default=1)
@@ -207,6 +386,8 @@ def main():
   parser.add_argument('--warmup', type=int, default=3)
   parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   parser.add_argument('--no-cpu-baseline', action='store_true')
+  parser.add_argument('--no-extra', action='store_true',
+                      help='skip BASELINE configs 3-5 (the `extra` block)')
   args = parser.parse_args()
   rank = int(os.environ.get('RANK', '0'))
   world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -222,9 +403,8 @@ def main():
     sys.exit('bench.py: no CUDA device; this backend has no CPU path')
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   distributed = world > 1
-  # one process per GPU: keep each on its GPU's NUMA node, or the end-to-end
-  # leg's host buffers of half the ranks sit across the socket interconnect
-  # (one rank keeps every core: the CPU baseline runs on all of them)
+  # one process per GPU: keep each on its GPU's NUMA node where the machine
+  # exposes one (the pool's KVM guests report a single node: nothing to bind)
   numa_node = soda_cuda.bind_host_to_gpu(local_rank) if distributed else None
   torch.cuda.set_device(local_rank)
   if distributed:
@@ -300,32 +480,80 @@ def main():
   # slab runs launch faces and interior separately: a "pass" is one sweep of
   # the whole slab by the depth-T kernel, however many launches it took
   depth = depth_planned or stats['depth']
+  if distributed:
+    del runner
+  torch.cuda.empty_cache()
 
   # ---- end to end through the C ABI with host buffers ------------------------
-  host_in = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-  host_out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-  host_in.copy_(dev_in)
-  torch.cuda.synchronize()
-  np_in, np_out = host_in.numpy(), host_out.numpy()
-  e2e_steps = max(2, min(args.steps, 5))
-  for _ in range(2):
-    library.run([np_in], [np_out])
+  # One call on the global grid.  N > 1: rank 0 makes it with
+  # "devices=0,..,N-1" (the runtime cuts the host arrays into one slab per
+  # device, soda_cuda_runtime.cu run_sharded); the other ranks wait.
+  e2e = None
   barrier()
-  t0 = time.perf_counter()
-  for _ in range(e2e_steps):
-    library.run([np_in], [np_out])       # H2D + all launches + D2H, synchronous
-  torch.cuda.synchronize()
-  e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+  if rank == 0:
+    global_shape = (dims[1] * world, dims[0])
+    host_in = torch.empty(global_shape, dtype=torch.float32, pin_memory=True)
+    host_out = torch.empty(global_shape, dtype=torch.float32, pin_memory=True)
+    columns = torch.arange(dims[0], dtype=torch.float32)[None, :]
+    for r0 in range(0, global_shape[0], 4096):      # block-wise: no 8 GiB temps
+      block = torch.arange(r0, min(r0 + 4096, global_shape[0]),
+                           dtype=torch.float32)[:, None] + columns
+      host_in[r0:r0 + 4096] = block / torch.tensor(total, dtype=torch.float32)
+    np_in, np_out = host_in.numpy(), host_out.numpy()
+    devices = list(range(world)) if distributed else None
+    e2e_steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+      library.run([np_in], [np_out], devices=devices)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+      # H2D + all launches + D2H, synchronous
+      library.run([np_in], [np_out], devices=devices)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_stats = library.stats
+    slabs = library.slab_stats
+    # the result of the timed call against the device-resident run's: a
+    # checksum over the valid region (not a parity test, a did-it-run test)
+    e2e_value = cells * world * iterate / (e2e_ms * 1e6)
+    del host_in, host_out, np_in, np_out
+    ceiling_ms = copy_ceiling(world, cells * 4)
+    e2e = {'value': e2e_value, 'unit': 'GCell/s', 'ms_per_step': e2e_ms,
+           'h2d_bytes_per_step': cells * world * 4,
+           'd2h_bytes_per_step': cells * world * 4,
+           'h2d_ms': e2e_stats['h2d_ms'], 'd2h_ms': e2e_stats['d2h_ms'],
+           'kernel_ms': e2e_stats['kernel_ms'], 'steps': e2e_steps,
+           'launches_per_step': e2e_stats['launches'],
+           'api': 'soda_cuda_run (C ABI form of jacobi2d(buffer_t*, '
+                  'buffer_t*, const char*)), pinned host buffers, ONE call '
+                  'on the global %d x %d grid%s' % (
+                      dims[0], dims[1] * world,
+                      ', config "devices=%s": one slab per device' % ','.join(
+                          map(str, devices)) if devices else ''),
+           'per_slab': [{k: s[k] for k in ('h2d_ms', 'd2h_ms', 'kernel_ms',
+                                           'launches')} for s in slabs],
+           'copy_ceiling': {
+               'ms': ceiling_ms,
+               'gb_per_s_each_direction': cells * world * 4 / (ceiling_ms * 1e6),
+               'e2e_fraction_of_ceiling': ceiling_ms / e2e_ms,
+               'what': 'the same %d x %.2f GB to the devices and as much '
+                       'back at once, cudaMemcpyAsync from pinned memory, no '
+                       'compute: the host<->device capacity of this machine '
+                       'at %d device(s)' % (world, cells * 4 / 1e9, world)},
+           'numa_node_rank0': numa_node}
   barrier()
-  e2e_stats = library.stats
-  e2e_value = cells * world * iterate / (e2e_ms * 1e6)
+
+  peak, peak_kind = measured_hbm_gbs()
+  # ---- BASELINE configs 3-5 and the multi-GPU parity check (not timed in
+  # ms_per_step) ---------------------------------------------------------------
+  parity = sharded_parity(rank, world, barrier) if distributed else None
+  extra = None if args.no_extra else run_extra(rank, world, barrier,
+                                               max_over_ranks, peak)
 
   if rank != 0:
     if distributed:
       dist.destroy_process_group()
     return
 
-  peak, peak_kind = measured_hbm_gbs()
   launch_ms = ms_per_step / passes_per_step
   achieved = cells * BYTES_PER_CELL / (launch_ms * 1e6)        # GB/s
   traffic = None
@@ -341,23 +569,20 @@ def main():
       'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
       'dtype': 'f32',
       'data': 'synthetic (reference initialiser pattern, host.py:1033-1051)',
-      'config': dict(workload_config(world), temporal_depth=depth,
-                     launches_per_step=launches_per_step,
+      'config': workload_config(world),
+      'kernel': dict(temporal_depth=depth, launches_per_step=launches_per_step,
                      passes_per_step=passes_per_step,
                      threads=stats['threads'], smem_bytes=stats['smem_bytes'],
                      tma=bool(stats['used_tma'])),
-      'e2e': {'value': e2e_value, 'unit': 'GCell/s', 'ms_per_step': e2e_ms,
-              'h2d_bytes_per_step': cells * 4, 'd2h_bytes_per_step': cells * 4,
-              'h2d_ms': e2e_stats['h2d_ms'], 'd2h_ms': e2e_stats['d2h_ms'],
-              'kernel_ms': e2e_stats['kernel_ms'], 'steps': e2e_steps,
-              'api': 'soda_cuda_run (C ABI form of jacobi2d(buffer_t*, '
-                     'buffer_t*, const char*)), pinned host buffers; one '
-                     'independent 16384 x 16384 run per GPU',
-              'numa_node_rank0': numa_node},
+      'e2e': e2e,
       'gpu_launches': launches_per_step * args.steps,
       'roofline': {
           'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
           'frac': achieved / peak, 'traffic': traffic,
+          'traffic_source': 'profiles/traffic.json: dram__bytes_read.sum + '
+                            'dram__bytes_write.sum of one launch of this '
+                            'kernel from an `ncu --set full` capture of this '
+                            'command (not measured in this run)',
           'peak_source': peak_kind + ' (MEASURED_PEAKS.json hbm_gbs)',
           'kernel': 'soda_jacobi2d_d%d<true>' % depth,
           'algorithmic_bytes_per_launch': cells * BYTES_PER_CELL,
@@ -368,6 +593,10 @@ def main():
                                  (ms_per_step * 1e6))},
       'clocks': clocks,
   }
+  if parity is not None:
+    result['multi_gpu_parity'] = parity
+  if extra is not None:
+    result['extra'] = extra
   if not args.no_cpu_baseline and world == 1:
     cores = os.cpu_count() or 1
     cpu_value, cpu_seconds = cpu_port_gcells(CPU_SAMPLE_ITERATE, cores)

@@ -13,7 +13,8 @@
  *
  *    so the reference's generated test harness `<app>_test`
  *    (host.py:984-1167) links against it unmodified.  `xclbin` is an opaque
- *    string for the FPGA flow; here it is ignored (NULL or "" are fine).
+ *    string for the FPGA flow; here NULL or "" are fine, and "devices=0,1"
+ *    spreads a run on host buffers over several GPUs (see soda_cuda_run).
  *
  * 2. The `extern "C"` functions below, which are what a foreign-function
  *    binding (ctypes: soda/cuda.py; cgo/JNI stubs: INTEGRATION.md) loads.
@@ -102,6 +103,28 @@ int soda_cuda_window_of(int output, int iterate, int32_t lo[4], int32_t hi[4]);
  * valid region are written as 0. */
 int soda_cuda_run(buffer_t* const* inputs, buffer_t* const* outputs,
                   const char* config);
+
+/* Several GPUs behind the same call.  `config` — the `xclbin` string of
+ * `<app>()`, opaque to the FPGA flow (the call site is the single
+ * `<app>(...)` of the reference harness, host.py:1068-1070) — may contain
+ * "devices=0,1,2,3" (ordinals, repeats allowed) or "devices=all"; the
+ * environment variable SODA_CUDA_DEVICES means the same when the string does
+ * not say.  HOST buffers are then cut into one slab per listed device along
+ * the streamed (last) dimension; every device loads its slab plus ghost rows
+ * of the whole run's reach over its own PCIe link, runs all iterations
+ * without talking to the others, and writes its own rows back: the result is
+ * bit-identical to the one-device run.  (Device buffers live on one device;
+ * for them the list is ignored.  Device-resident multi-GPU runs with a halo
+ * exchange per launch are soda/cuda_slab.py.)
+ * soda_cuda_shard_plan reports that cut for a grid of extents `dims` (no
+ * device needed): slab r owns rows [own_begin[r], own_end[r]) and holds
+ * [local_begin[r], local_end[r]); returns the number of slabs used (<=
+ * n_slabs).  soda_cuda_slab_stats: how many slabs the last run had (0: not
+ * sharded) and, for 0 <= index < that, what slab `index` did. */
+int soda_cuda_shard_plan(const int32_t* dims, int n_slabs,
+                         int32_t* local_begin, int32_t* local_end,
+                         int32_t* own_begin, int32_t* own_end);
+int soda_cuda_slab_stats(int index, soda_cuda_stats_t* out);
 
 /* `param` statements (small constant arrays; reference grammar.py:38, passed
  * after the outputs by the reference entry, header.py:57-60).  A param is a

@@ -100,6 +100,10 @@ enum {
 };
 
 // `<app>(buffer_t*..., const char*)`: host or device buffers, bounds query.
+// `config` (the reference's opaque `xclbin` argument) may hold
+// "devices=0,1,..": host buffers are then cut into one slab per listed device
+// along the streamed dimension (SODA_CUDA_DEVICES does the same from the
+// environment; "all" = every visible device).
 int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
                 buffer_t* const* outputs, const char* config,
                 buffer_t* const* params = nullptr);
@@ -146,7 +150,20 @@ int ipc_open(const unsigned char handle[64], void** base);
 int ipc_close(void* base);
 int copy_async(void* dst, const void* src, uint64_t bytes, cudaStream_t stream);
 
+// How a run on host buffers over `n_slabs` devices cuts the streamed
+// dimension: slab r owns rows [own_begin[r], own_end[r]) and holds rows
+// [local_begin[r], local_end[r]) — its own plus ghost rows of the whole run's
+// reach on the sides where the grid continues.  Returns the slab count
+// actually used (thin grids use fewer).  Needs no device.
+int shard_plan(const ProgramDesc& prog, const int32_t* dims, int n_slabs,
+               int32_t* local_begin, int32_t* local_end, int32_t* own_begin,
+               int32_t* own_end);
+
 const soda_cuda_stats_t* last_stats();
+
+// Slabs of the last sharded run (0 if it was not sharded); `out`, if given
+// and `index` is in range, receives what that slab's device did.
+int slab_stats(int index, soda_cuda_stats_t* out);
 
 // Frees the cached device buffers.
 void release_all();

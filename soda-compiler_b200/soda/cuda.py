@@ -197,6 +197,9 @@ class Library:
         ('soda_cuda_copy_async', c_int,
          [c_void_p, c_void_p, ctypes.c_uint64, c_void_p]),
         ('soda_cuda_last_stats', ctypes.POINTER(Stats), []),
+        ('soda_cuda_shard_plan', c_int,
+         [i32p, c_int, i32p, i32p, i32p, i32p]),
+        ('soda_cuda_slab_stats', c_int, [c_int, ctypes.POINTER(Stats)]),
         ('soda_cuda_release', None, []),
     ):
       fn = getattr(lib, name)
@@ -255,6 +258,28 @@ class Library:
 
   def release(self):
     self._lib.soda_cuda_release()
+
+  def shard_plan(self, dims, n_slabs):
+    """How ``run(..., devices=[..])`` cuts a grid: per slab ``(local_begin,
+    local_end, own_begin, own_end)`` rows of the streamed dimension."""
+    arrays = [(ctypes.c_int32 * n_slabs)() for _ in range(4)]
+    used = self._lib.soda_cuda_shard_plan(
+        (ctypes.c_int32 * 4)(*(list(dims) + [1] * (4 - len(dims)))), n_slabs,
+        *arrays)
+    if used < 0:
+      raise CudaError('soda_cuda_shard_plan', used)
+    return [tuple(a[r] for a in arrays) for r in range(used)]
+
+  @property
+  def slab_stats(self):
+    """Per slab of the last sharded run (empty if it was not sharded)."""
+    count = self._lib.soda_cuda_slab_stats(-1, None)
+    result = []
+    for index in range(count):
+      stats = Stats()
+      self._lib.soda_cuda_slab_stats(index, ctypes.byref(stats))
+      result.append(stats.as_dict())
+    return result
 
   # ---- buffers ----
   def _describe(self, array, haoda_type, what):
@@ -319,8 +344,12 @@ class Library:
     if code:
       raise CudaError('soda_cuda_set_params(%s)' % self.app_name, code)
 
-  def run(self, inputs, outputs=None, params=None):
+  def run(self, inputs, outputs=None, params=None, devices=None):
     """Run the whole program (all ``iterate`` iterations); returns outputs.
+
+    ``devices``: CUDA ordinals (or ``'all'``) to spread a run on HOST arrays
+    over — one slab of the streamed dimension per entry, bit-identical to
+    the one-device run (soda_cuda_run's "devices=" config).
 
     ``inputs`` in program order.  ``outputs``: arrays to fill, or None to
     allocate them like the first input (numpy -> numpy, torch -> torch).
@@ -353,6 +382,10 @@ class Library:
         *[ctypes.pointer(b) for b in in_bufs])
     out_ptrs = (ctypes.POINTER(BufferT) * len(out_bufs))(
         *[ctypes.pointer(b) for b in out_bufs])
+    config = None
+    if devices is not None:
+      config = ('devices=%s' % (devices if isinstance(devices, str) else
+                                ','.join(str(d) for d in devices))).encode()
     if self.params:
       arrays = self._param_arrays(params)
       param_bufs = []
@@ -369,9 +402,9 @@ class Library:
       param_ptrs = (ctypes.POINTER(BufferT) * len(param_bufs))(
           *[ctypes.pointer(b) for b in param_bufs])
       code = self._lib.soda_cuda_run_params(in_ptrs, out_ptrs, param_ptrs,
-                                            None)
+                                            config)
     else:
-      code = self._lib.soda_cuda_run(in_ptrs, out_ptrs, None)
+      code = self._lib.soda_cuda_run(in_ptrs, out_ptrs, config)
     if code:
       raise CudaError('soda_cuda_run(%s)' % self.app_name, code)
     return list(outputs)
@@ -535,8 +568,9 @@ def compile_stencil(stencil, **kwargs):
   return load(build(stencil, **kwargs))
 
 
-def run(stencil, arrays, params=None, **kwargs):
-  """Run ``stencil`` on ``arrays`` on the current CUDA device.
+def run(stencil, arrays, params=None, devices=None, **kwargs):
+  """Run ``stencil`` on ``arrays`` on the current CUDA device (or, for host
+  arrays, sharded over ``devices``).
 
   ``arrays``: the inputs in program order, or a dict by input name (which may
   also hold the param arrays by name).  Returns the outputs in program order
@@ -547,6 +581,6 @@ def run(stencil, arrays, params=None, **kwargs):
     inputs = [arrays[name] for name, _ in library.inputs]
     if params is None and library.params:
       params = [arrays[name] for name, _, _ in library.params]
-    outputs = library.run(inputs, params=params)
+    outputs = library.run(inputs, params=params, devices=devices)
     return {name: out for (name, _), out in zip(library.outputs, outputs)}
-  return library.run(list(arrays), params=params)
+  return library.run(list(arrays), params=params, devices=devices)

@@ -98,3 +98,34 @@ def test_argument_checks(library):
     library.run([np.zeros((4, 64, 64), dtype=np.float32)])
   with pytest.raises(ValueError):
     library.run([np.zeros((64, 64), dtype=np.float32)[:, ::2]])
+
+
+def test_per_output_windows_are_exported(library):
+  assert library.window_of(0) == ((-3, -3), (3, 3))
+  assert library.valid_regions((100, 50), 1) == [[(1, 99), (1, 49)]]
+  with pytest.raises(soda_cuda.CudaError):
+    library.window_of(1)
+
+
+@pytest.mark.parametrize('rows,n', [(1000, 4), (1001, 3), (50, 8), (16384, 8),
+                                    (7, 2)])
+def test_shard_plan_covers_the_grid_with_ghosts_of_the_whole_run(library, rows,
+                                                                 n):
+  """soda_cuda_shard_plan (no device needed): the slabs of a sharded run own
+  disjoint row ranges that cover the grid, and hold ghost rows of the whole
+  run's reach (3 iterations of jacobi2d: 3 rows) wherever the grid continues."""
+  plan = library.shard_plan((256, rows), n)
+  assert 1 <= len(plan) <= n
+  lo, hi = library.window()
+  ghost_lo, ghost_hi = max(0, -lo[-1]), max(0, hi[-1])
+  previous = 0
+  for local_begin, local_end, own_begin, own_end in plan:
+    assert own_begin == previous and own_end > own_begin
+    assert local_begin == max(0, own_begin - ghost_lo)
+    assert local_end == min(rows, own_end + ghost_hi)
+    previous = own_end
+  assert previous == rows
+  if len(plan) > 1:       # never more ghost than grid
+    assert min(b - a for _, _, a, b in plan) >= ghost_lo + ghost_hi
+  sizes = [b - a for _, _, a, b in plan]
+  assert max(sizes) - min(sizes) <= 1

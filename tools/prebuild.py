@@ -81,6 +81,9 @@ def main():
       jobs.append(('multi%d' % seed, random_programs.multi_stencil(seed), {}))
     import test_math_calls
     jobs.append(('calls', core.Stencil.from_text(test_math_calls.TEXT), {}))
+    import test_sharded_run_gpu
+    for name, iterate, _ in test_sharded_run_gpu.CASES:
+      jobs.append((name, iterate, {}))
     import wide_type_programs
     for name, _, options in wide_type_programs.CASES:
       jobs.append((name, wide_type_programs.stencil_of(name), options))
