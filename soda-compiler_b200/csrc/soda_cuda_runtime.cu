@@ -1438,6 +1438,8 @@ void release_all() {
     }
     lane->params_version = 0;
   }
+  g_params_host.clear();      // params must be set again before a launch
+  g_params_version = 0;
   cudaSetDevice(caller_device);
 }
 

@@ -106,6 +106,8 @@ def main():
     stencil = job[1] if hasattr(job[1], 'app_name') else None
     return (job[0], stencil.iterate if stencil else job[1],
             sorted(job[2].items()))
+  from soda import fpga_layout
+  kept = {os.path.dirname(os.path.abspath(fpga_layout.build()))}
   for group, env in ((jobs, None), (untuned, '0')):
     unique = []
     for job in group:
@@ -116,7 +118,20 @@ def main():
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as pool:
       for job, path in zip(unique, pool.map(build, unique)):
         print('%-40s %s' % (label(job), os.path.relpath(path, ROOT)))
+        kept.add(os.path.dirname(os.path.abspath(path)))
     os.environ.pop('SODA_CUDA_TUNED', None)
+  if not args:
+    # a full prebuild names every library the tests and benches load: builds
+    # of earlier source states (other hashes) only fatten the GPU snapshot
+    import re
+    stale = [os.path.join(soda_cuda.DEFAULT_BUILD_DIR, name)
+             for name in os.listdir(soda_cuda.DEFAULT_BUILD_DIR)
+             if re.fullmatch(r'\w+-[0-9a-f]{12}', name)]
+    stale = [path for path in stale if path not in kept and any(
+        f.startswith('libsoda_') for f in os.listdir(path))]
+    for path in stale:
+      shutil.rmtree(path, ignore_errors=True)
+    print('removed %d stale build(s)' % len(stale))
 
 
 if __name__ == '__main__':
