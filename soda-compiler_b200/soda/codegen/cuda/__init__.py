@@ -31,7 +31,7 @@ from soda.codegen.cuda import tuned as tuned_mod
 
 SUPPORTED_TYPES = {
     'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32', 'int64',
-    'float', 'float32', 'double', 'float64'}
+    'float', 'float32', 'double', 'float64', 'half'}
 SMEM_LIMIT = 227 * 1024
 REG_HISTORY_BUDGET = 80   # registers per thread held across steps (2-D)
 REG_HISTORY_3D = 64       # 3-D: above this, one vector per thread
@@ -82,6 +82,18 @@ def add_arguments(parser):
       'this machine (times the candidates of soda.cuda_tune and records the '
       'winner in tuned.json before emitting); the GPU counterpart of '
       'exploring --tile-size / --unroll-factor')
+  parser.add_argument(
+      '--cuda-fast', action='store_true', dest='cuda_fast',
+      help='emit the kernels for the non-exact build (FMA contraction, '
+      'approximate division, a / sqrt(x) as a refined rsqrt; within 1e-6 '
+      'relative or 2 ulp of the reference, not bit-exact): the kernel file '
+      'defines SODA_CUDA_FAST_MATH; compile it WITHOUT -fmad=false and with '
+      '-prec-div=false -prec-sqrt=false')
+  parser.add_argument(
+      '--cuda-exact', action='store_false', dest='cuda_fast',
+      help='emit the kernels for the bit-exact build (the default): '
+      'reference operation order, no FMA contraction; compile with '
+      '-fmad=false')
   parser.add_argument(
       '--cuda-style', type=str, dest='cuda_style', choices=['reg', 'ring'],
       help='kernel family: `reg` keeps the streamed window of every tensor '
@@ -373,12 +385,21 @@ def make_schedules(program, options=None):
   return [make_schedule(program, depth, options) for depth in depths]
 
 
-def print_kernel(program, schedules, kernel_file):
+def print_kernel(program, schedules, kernel_file, fast_math=False):
   p = util.Printer(kernel_file)
   p.println('// CUDA kernels of SODA program `%s` for sm_100a.' %
             program.app_name)
   p.println('// Generated by sodac --cuda-kernel; do not edit.')
-  p.println('// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false')
+  if fast_math:
+    p.println('// Build (--cuda-fast, NOT bit-exact): nvcc -gencode '
+              'arch=compute_100a,code=sm_100a')
+    p.println('//   -prec-div=false -prec-sqrt=false   (and no -fmad=false)')
+    p.println('#ifndef SODA_CUDA_FAST_MATH')
+    p.println('#define SODA_CUDA_FAST_MATH 1')
+    p.println('#endif')
+  else:
+    p.println('// Build: nvcc -gencode arch=compute_100a,code=sm_100a '
+              '-fmad=false')
   p.println('#include "soda_cuda_device.cuh"')
   p.println('#include "soda_cuda_runtime.h"')
   p.println()
@@ -436,7 +457,8 @@ def print_code(stencil, args):
       cuda_tune.record(program, dims, results[0][0], results[0][1])
   if kernel_file is not None:
     schedules = make_schedules(program, Options.from_args(args))
-    _emit(kernel_file, lambda f: print_kernel(program, schedules, f))
+    fast = bool(getattr(args, 'cuda_fast', False))
+    _emit(kernel_file, lambda f: print_kernel(program, schedules, f, fast))
   if host_file is not None:
     _emit(host_file, lambda f: host_mod.print_code(program, f))
   if header_file is not None:

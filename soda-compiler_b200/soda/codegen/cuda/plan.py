@@ -699,6 +699,52 @@ class RegSchedule(Schedule):
     reach = [abs(self.plane_offset(off)) for node in self.stage_nodes
              for _, off in node.loads if self.via_smem(off)]
     self.guard_elems = max(reach) if reach else 0
+    self._measure_needs()
+
+  def _measure_needs(self):
+    """Rows of the tile, in the tiled dimensions other than 0, where each
+    stage replica has to be computed at all: the rows this tile owns, widened
+    on the way back from the outputs by the offsets of the loads in between.
+    A warp spans the tile in dimension 0 and sits at one position in the
+    others, so whole warps skip the stages of the halo rows that no owned
+    cell depends on (garbage tolerance makes computing them harmless, not
+    necessary): ``node.need[d - 1] = (lo, hi)`` in tile coordinates."""
+    dims = range(1, self.sdim)
+    for node in self.nodes:
+      node.need = None
+    for node in self.outputs:
+      node.need = [(self.tile_halo_lo[d], self.tile[d] - self.tile_halo_hi[d])
+                   for d in dims]
+    for node in reversed(self.stage_nodes):
+      if node.need is None:      # feeds nothing that is stored
+        node.need = [(0, 0) for _ in dims]
+      for parent, off in node.loads:
+        if parent.is_input:
+          continue
+        mine = [(max(0, lo + off[d]), min(self.tile[d], hi + off[d]))
+                for d, (lo, hi) in zip(dims, node.need)]
+        if any(hi <= lo for lo, hi in mine):
+          continue
+        if parent.need is None:
+          parent.need = mine
+        else:
+          parent.need = [(min(a, lo), max(b, hi))
+                         for (a, b), (lo, hi) in zip(parent.need, mine)]
+
+  SKIP_WEIGHT = 8    # operations per cell from which a skip test pays
+
+  def skips_rows(self, node):
+    """Does ``node`` have tile rows (dims 1..) on which it need not run, and
+    is it heavy enough for the test to pay?  (A one-subtraction stage costs
+    less than its predicate, and conditional results held across the branch
+    cost registers: denoise3d spilled with every stage predicated.)"""
+    if not any((lo, hi) != (0, self.tile[d + 1])
+               for d, (lo, hi) in enumerate(node.need)):
+      return False
+    _, text = node.stage.render(lambda load: 'x')
+    weight = (sum(text.count(op) for op in '+-*') + 8 * text.count('/') +
+              8 * text.count('sqrt'))
+    return weight >= self.SKIP_WEIGHT
 
   def describe(self):
     lines = ['%sregister-streaming schedule %s: depth %d, tile %s x %d/block, '

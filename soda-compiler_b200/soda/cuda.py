@@ -38,7 +38,8 @@ NUMPY_TYPES = {
     'uint8': np.uint8, 'uint16': np.uint16, 'uint32': np.uint32,
     'uint64': np.uint64, 'int8': np.int8, 'int16': np.int16,
     'int32': np.int32, 'int64': np.int64, 'float': np.float32,
-    'float32': np.float32, 'double': np.float64, 'float64': np.float64}
+    'float32': np.float32, 'double': np.float64, 'float64': np.float64,
+    'half': np.float16}
 
 ERROR_NAMES = {
     -1: 'generic_error', -3: 'bad_elem_size', -4: 'access_out_of_bounds',
@@ -82,12 +83,12 @@ class Stats(ctypes.Structure):
 
 # --- build --------------------------------------------------------------------
 
-def generate_sources(stencil, options=None):
+def generate_sources(stencil, options=None, fast_math=False):
   """``(program, kernel source, host source)`` for a Stencil."""
   program = plan_mod.extract_program(stencil)
   schedules = codegen.make_schedules(program, options)
   kernel, host = io.StringIO(), io.StringIO()
-  codegen.print_kernel(program, schedules, kernel)
+  codegen.print_kernel(program, schedules, kernel, fast_math)
   host_gen.print_code(program, host)
   return program, kernel.getvalue(), host.getvalue()
 
@@ -97,7 +98,10 @@ def nvcc_command(sources, output, fast_math=False, extra=()):
            '-I', CSRC_DIR, '-I', INCLUDE_DIR]
   # exact mode: no FMA contraction, so float results match the reference's
   # x86-64 golden loop bit for bit
-  flags += ['-DSODA_CUDA_FAST_MATH'] if fast_math else ['-fmad=false']
+  # fast mode (tolerance-tested only): FMA contraction, approximate division
+  # (div.approx: 2 ulp) and square root, a / sqrt(x) as a refined MUFU.RSQ
+  flags += (['-DSODA_CUDA_FAST_MATH', '-prec-div=false', '-prec-sqrt=false']
+            if fast_math else ['-fmad=false'])
   return (['nvcc'] + ARCH_FLAGS + flags + list(extra) + list(sources) +
           ['-o', output])
 
@@ -113,7 +117,8 @@ def build(stencil, build_dir=None, options=None, fast_math=False,
   if shutil.which('nvcc') is None:
     raise RuntimeError('nvcc not found: the SODA CUDA backend compiles its '
                        'kernels offline and has no other execution path')
-  program, kernel_src, host_src = generate_sources(stencil, options)
+  program, kernel_src, host_src = generate_sources(stencil, options,
+                                                   fast_math)
   runtime = os.path.join(CSRC_DIR, 'soda_cuda_runtime.cu')
   digest = hashlib.sha256()
   for text in (kernel_src, host_src, str(fast_math)):

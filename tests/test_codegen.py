@@ -52,6 +52,21 @@ def test_stdin_and_iterate_override():
   assert 'soda_jacobi2d_d2(' in done.stdout      # remainder 6 % 4
 
 
+def test_fast_and_exact_switches():
+  """--cuda-fast marks the kernel file for the tolerance-tested build;
+  --cuda-exact (the default) does not."""
+  fast = sodac(common.bench_path('denoise2d'), '--cuda-fast', '--cuda-kernel',
+               '-')
+  assert fast.returncode == 0, fast.stderr
+  assert '#define SODA_CUDA_FAST_MATH 1' in fast.stdout
+  assert '-prec-div=false' in fast.stdout
+  for flags in ([], ['--cuda-exact']):
+    exact = sodac(common.bench_path('denoise2d'), '--cuda-kernel', '-', *flags)
+    assert exact.returncode == 0, exact.stderr
+    assert 'SODA_CUDA_FAST_MATH' not in exact.stdout
+    assert '-fmad=false' in exact.stdout
+
+
 def test_errors_exit_1():
   assert sodac('-', '--cuda-kernel', '-', stdin='kernel: broken').returncode == 1
   done = sodac(common.bench_path('denoise2d'), '--iterate', '2',
