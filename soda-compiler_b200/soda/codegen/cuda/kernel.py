@@ -81,21 +81,7 @@ def _render_stage(stage, ref_code):
   """``Stage.render`` for device code: DSL calls go through the soda_fn_*
   wrappers and let variables get a prefix that cannot clash with the
   kernel's own identifiers."""
-  let_names = {let.name for let in stage.lets}
-
-  def swap(obj, _):
-    kind = type(obj).__name__
-    if kind == 'Ref':
-      return plan_mod.Code(ref_code(stage.load_of(obj)))
-    if kind == 'Call' and not obj.name.startswith('soda_fn_'):
-      obj.name = 'soda_fn_' + obj.name
-    elif kind == 'Var' and obj.name in let_names:
-      obj.name = 'let_' + obj.name
-    return obj
-  lets = ['const %s let_%s = %s;' % (
-      let.c_type, let.name, let.expr.visit(swap).c_expr)
-          for let in stage.lets]
-  return lets, stage.expr.visit(swap).c_expr
+  return stage.render(ref_code, call_prefix='soda_fn_', let_prefix='let_')
 
 
 def emit_kernel(p, sched):

@@ -104,21 +104,8 @@ def _log2(n):
 
 def _render(stage, ref_code, k):
   """``(let lines, expression)`` of cell ``k`` of the thread's vector."""
-  let_names = {let.name for let in stage.lets}
-
-  def swap(obj, _):
-    kind = type(obj).__name__
-    if kind == 'Ref':
-      return plan_mod.Code(ref_code(stage.load_of(obj), k))
-    if kind == 'Call' and not obj.name.startswith('soda_fn_'):
-      obj.name = 'soda_fn_' + obj.name
-    elif kind == 'Var' and obj.name in let_names:
-      obj.name = 'let_' + obj.name
-    return obj
-  lets = ['const %s let_%s = %s;' % (
-      let.c_type, let.name, let.expr.visit(swap).c_expr)
-          for let in stage.lets]
-  return lets, stage.expr.visit(swap).c_expr
+  return stage.render(lambda load: ref_code(load, k), call_prefix='soda_fn_',
+                      let_prefix='let_')
 
 
 _INT_TYPES = {'uint8', 'uint16', 'uint32', 'uint64', 'int8', 'int16', 'int32',
@@ -303,14 +290,6 @@ class _Emitter:
     p.println('int gx[%d];' % VPT)
     for d in range(1, s):
       p.println('int gc%d[%d];' % (d, VPT))
-    self.skipping = [n for n in sched.stage_nodes
-                     if not self.flat and sched.skips_rows(n)]
-    if self.skipping:
-      p.println('// bit n: stage n has to run on the tile row of this vector '
-                '(warp-uniform:')
-      p.println('// a warp spans dimension 0); halo rows no owned cell depends '
-                'on are skipped')
-      p.println('unsigned act[%d];' % VPT)
     p.println('#pragma unroll')
     p.println('for (int j = 0; j < %d; ++j)' % VPT)
     p.do_scope()
@@ -344,14 +323,6 @@ class _Emitter:
           d, d, d))
     p.println('goff[j] = off;')
     p.println('xin[j] = inside && gx[j] >= 0 && gx[j] + %d <= a.dims[0];' % V)
-    if self.skipping:
-      p.println('unsigned on = 0;')
-      for node in self.skipping:
-        cond = ' && '.join('c%d >= %d && c%d < %d' % (d + 1, lo, d + 1, hi)
-                           for d, (lo, hi) in enumerate(node.need))
-        p.println('if (%s) on |= %du;   // %s' % (
-            cond, 1 << sched.stage_nodes.index(node), node.ident))
-      p.println('act[j] = on;')
     p.println('unsigned m = 0;')
     for n in range(len(sched.outputs)):
       p.println('unsigned v%d = 0;' % n)
@@ -714,10 +685,6 @@ class _Emitter:
         p.println('%s[j] = soda::shfl_down<%s>(%s, %d);' % (
             var, self.ctype(parent), src, lanes))
 
-    skip = node in self.skipping
-    if skip:
-      p.println('if (act[j] & %du)' % (1 << sched.stage_nodes.index(node)))
-      p.do_scope()
     # operands read through shared memory: one window per (parent, offsets in
     # dims 1..), as in kernel.py
     groups = collections.OrderedDict()
@@ -841,10 +808,7 @@ class _Emitter:
       p.println('  if ((own[j] >> k) & 1u) op%d[j][k] = o[k];' % n)
       p.un_scope()
       p.un_scope()
-    if skip:
-      p.un_scope()
-    if node.output_index is not None:
-      p.println('op%d[j] += a.stride[%d];' % (node.output_index, s))
+      p.println('op%d[j] += a.stride[%d];' % (n, s))
     p.un_scope()
     p.un_scope()
 

@@ -55,16 +55,26 @@ class Code:
     return self
 
 
+def _is_call(obj):
+  return type(obj).__name__ == 'Call'
+
+
 class Stage:
-  """One local/output statement of one iteration."""
+  """One local/output statement of one iteration.
+
+  ``inlined`` maps the names of other stages to their Stage objects: a Ref to
+  one of them is not a load but that stage's own expression, spliced in at the
+  Ref's offset and rounded through the stage's declared type exactly as the
+  store into its array would (``inline_single_use`` builds such stages)."""
 
   def __init__(self, name, haoda_type, lets, expr, store_idx, is_output,
-               params=(), alias=None):
+               params=(), alias=None, inlined=None):
     self.params = frozenset(params)   # names of param arrays
     # replica name -> statement name: with iterate > 1 the Stencil IR calls
     # output k of the first iteration `<input k>_iter1` (reference
     # core.py:347-351), also where a later statement reads it
     self.alias = dict(alias or {})
+    self.inlined = dict(inlined or {})
     self.name = name
     self.haoda_type = haoda_type
     self.c_type = util.get_c_type(haoda_type)
@@ -73,40 +83,85 @@ class Stage:
     self.store_idx = tuple(store_idx)
     self.is_output = is_output
     self.loads = []           # unique Load, first-use order
-    for node in self.lets + (expr,):
-      node.visit(self._note_load)
+    for load in self.walk_loads():
+      if load not in self.loads:
+        self.loads.append(load)
 
-  def load_of(self, ref):
+  def load_of(self, ref, shift=None):
+    """The Load a Ref of this statement stands for; ``shift`` displaces it
+    (the offset at which this statement is itself spliced into another)."""
     if ref.name in self.params:
       # a param is a small constant array indexed absolutely (the golden
       # loop reads `<name>_img[i][j]`, reference host.py:1095-1097)
       return Load(ref.name, tuple(ref.idx))
-    return Load(self.alias.get(ref.name, ref.name),
-                tuple(a - b for a, b in zip(ref.idx, self.store_idx)))
+    off = tuple(a - b for a, b in zip(ref.idx, self.store_idx))
+    if shift is not None:
+      off = tuple(a + b for a, b in zip(off, shift))
+    return Load(self.alias.get(ref.name, ref.name), off)
 
-  def _note_load(self, obj, _):
-    if _is_ref(obj):
-      load = self.load_of(obj)
-      if load not in self.loads:
-        self.loads.append(load)
+  def walk_loads(self, shift=None):
+    """Every load of the statement in first-use order, through inlined
+    statements, with repeats."""
+    found = []
 
-  def render(self, ref_code):
+    def note(obj, _):
+      if _is_ref(obj):
+        load = self.load_of(obj, shift)
+        if load.parent in self.inlined:
+          found.extend(self.inlined[load.parent].walk_loads(load.off))
+        else:
+          found.append(load)
+    for node in tuple(let.expr for let in self.lets) + (self.expr,):
+      node.visit(note)
+    return found
+
+  def calls(self):
+    names = []
+
+    def note(obj, _):
+      if _is_call(obj):
+        names.append(obj.name)
+    for node in tuple(let.expr for let in self.lets) + (self.expr,):
+      node.visit(note)
+    return names
+
+  def render(self, ref_code, call_prefix='', let_prefix='', shift=None,
+             cast=None):
     """``(let lines, expression)`` as C, each Ref replaced by ``ref_code(load)``.
 
     The expression text is the IR's own ``c_expr`` lowering of the tree with
     Refs swapped for storage accesses — the recipe of the golden loop's
     ``mutate_load_for_host`` (host.py:1093-1117), so operator order and
-    parenthesisation are the reference's, quirks included.
+    parenthesisation are the reference's, quirks included.  A Ref to an
+    inlined statement becomes ``cast(its C type, its expression)`` — by
+    default ``soda::store_cast<T>(..)``, the rounding its array would apply.
+    ``call_prefix`` / ``let_prefix`` rename math calls and let variables.
     """
+    if cast is None:
+      cast = lambda c_type, text: 'soda::store_cast<%s>(%s)' % (c_type, text)
+    let_names = {let.name for let in self.lets}
+
     def swap(obj, _):
       if _is_ref(obj):
-        return Code(ref_code(self.load_of(obj)))
+        load = self.load_of(obj, shift)
+        if load.parent in self.inlined:
+          other = self.inlined[load.parent]
+          _, text = other.render(ref_code, call_prefix, let_prefix, load.off,
+                                 cast)
+          return Code(cast(other.c_type, text))
+        return Code(ref_code(load))
+      if call_prefix and _is_call(obj) and not obj.name.startswith(
+          call_prefix):
+        obj.name = call_prefix + obj.name
+      elif (let_prefix and type(obj).__name__ == 'Var' and
+            obj.name in let_names):
+        obj.name = let_prefix + obj.name
       return obj
     # like the golden loop (host.py:1111-1114) the right-hand side keeps its
     # parentheses: the IR's `unparenthesize` is not bracket-matching and would
     # turn `(a == b) & (c)` into `a == b) & (c`
-    lets = ['const %s %s = %s;' % (let.c_type, let.name,
-                                   let.expr.visit(swap).c_expr)
+    lets = ['const %s %s%s = %s;' % (let.c_type, let_prefix, let.name,
+                                     let.expr.visit(swap).c_expr)
             for let in self.lets]
     return lets, self.expr.visit(swap).c_expr
 
@@ -264,6 +319,49 @@ def param_code(program, load):
   """Device code of a param load: a uniform read-only load the compiler
   hoists out of the streamed loop."""
   return '__ldg(prm_%s + %d)' % (load.parent, program.param_flat(load))
+
+
+def inline_single_use(program):
+  """``program`` with every local statement that is read exactly once — by
+  one statement, at one offset — spliced into its reader (None if there is
+  nothing to splice).
+
+  A local that is written only to be read back once costs a register history
+  (or a shared plane) from the step it is computed to the step it is used;
+  spliced in, it is evaluated where it is used, from operands its reader
+  mostly holds anyway (denoise3d: six differences, r0 and r1 — 100 of the
+  128 registers per thread were histories).  The value is the same: the
+  local's expression with the same operands in the same order, rounded
+  through the local's declared type as the store into its array rounds it.
+  Statements with math calls or let bindings stay (their lazily evaluated
+  forms, e.g. the exact `a / sqrt(x)`, are resolved by the store).
+  """
+  uses = collections.Counter()
+  for stage in program.stages:
+    for load in set(stage.walk_loads()):
+      uses[load.parent] += 1
+  by_name = {stage.name: stage for stage in program.stages}
+  chosen = [stage.name for stage in program.stages
+            if not stage.is_output and uses[stage.name] == 1 and
+            not stage.lets and not stage.calls() and not stage.inlined]
+  if not chosen:
+    return None
+  kept = []
+  rebuilt = {}
+  for stage in program.stages:       # dependency order: parents come first
+    inlined = {name: rebuilt.get(name, by_name[name]) for name in chosen
+               if any(load.parent == name for load in stage.loads)}
+    new = Stage(stage.name, stage.haoda_type, stage.lets, stage.expr,
+                stage.store_idx, stage.is_output, stage.params, stage.alias,
+                inlined) if inlined else stage
+    rebuilt[stage.name] = new
+    if stage.name not in chosen:
+      kept.append(new)
+  result = Program(program.app_name, program.dim, program.iterate,
+                   program.inputs, program.outputs, kept,
+                   params=program.param_stmts)
+  result.types = dict(program.types)    # the spliced locals keep their types
+  return result
 
 
 def extract_program(stencil):
@@ -552,7 +650,8 @@ def pairing_obstacle(program, depth):
     if haoda_type not in ('float', 'float32'):
       return '`%s` is %s, not float32' % (name, haoda_type)
   for stage in program.stages:
-    lets, expr = stage.render(lambda load: '')
+    lets, expr = stage.render(lambda load: '',
+                              cast=lambda c_type, text: '(%s)' % text)
     if lets:
       return 'let bindings'
     pos = 0
@@ -699,52 +798,6 @@ class RegSchedule(Schedule):
     reach = [abs(self.plane_offset(off)) for node in self.stage_nodes
              for _, off in node.loads if self.via_smem(off)]
     self.guard_elems = max(reach) if reach else 0
-    self._measure_needs()
-
-  def _measure_needs(self):
-    """Rows of the tile, in the tiled dimensions other than 0, where each
-    stage replica has to be computed at all: the rows this tile owns, widened
-    on the way back from the outputs by the offsets of the loads in between.
-    A warp spans the tile in dimension 0 and sits at one position in the
-    others, so whole warps skip the stages of the halo rows that no owned
-    cell depends on (garbage tolerance makes computing them harmless, not
-    necessary): ``node.need[d - 1] = (lo, hi)`` in tile coordinates."""
-    dims = range(1, self.sdim)
-    for node in self.nodes:
-      node.need = None
-    for node in self.outputs:
-      node.need = [(self.tile_halo_lo[d], self.tile[d] - self.tile_halo_hi[d])
-                   for d in dims]
-    for node in reversed(self.stage_nodes):
-      if node.need is None:      # feeds nothing that is stored
-        node.need = [(0, 0) for _ in dims]
-      for parent, off in node.loads:
-        if parent.is_input:
-          continue
-        mine = [(max(0, lo + off[d]), min(self.tile[d], hi + off[d]))
-                for d, (lo, hi) in zip(dims, node.need)]
-        if any(hi <= lo for lo, hi in mine):
-          continue
-        if parent.need is None:
-          parent.need = mine
-        else:
-          parent.need = [(min(a, lo), max(b, hi))
-                         for (a, b), (lo, hi) in zip(parent.need, mine)]
-
-  SKIP_WEIGHT = 8    # operations per cell from which a skip test pays
-
-  def skips_rows(self, node):
-    """Does ``node`` have tile rows (dims 1..) on which it need not run, and
-    is it heavy enough for the test to pay?  (A one-subtraction stage costs
-    less than its predicate, and conditional results held across the branch
-    cost registers: denoise3d spilled with every stage predicated.)"""
-    if not any((lo, hi) != (0, self.tile[d + 1])
-               for d, (lo, hi) in enumerate(node.need)):
-      return False
-    _, text = node.stage.render(lambda load: 'x')
-    weight = (sum(text.count(op) for op in '+-*') + 8 * text.count('/') +
-              8 * text.count('sqrt'))
-    return weight >= self.SKIP_WEIGHT
 
   def describe(self):
     lines = ['%sregister-streaming schedule %s: depth %d, tile %s x %d/block, '

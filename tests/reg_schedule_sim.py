@@ -18,8 +18,6 @@ the emitter generates:
   0..chain-1 from the input, lane B chains iterations chain..depth-1 from the
   plane lane A's output stage produced one step earlier; lane B's output is
   what is stored;
-* 3-D: a stage runs only on the tile rows (dimensions 1..) that some owned
-  cell depends on (``node.need``); elsewhere it leaves garbage;
 * chunks with a lead-in, trips of whole periods, overlapping tiles, ownership
   and the valid region as in the kernel.
 
@@ -179,11 +177,6 @@ def run_schedule(sched, dims, chunk_rows, final=True):
               ok &= (got == want) & (want != GARBAGE)
             mine = _code(tag(node, lane), gcoord + [np.full(
                 plane, row - (sched.pair_lag if lane else 0))], dims)
-            # 3-D: whole warps skip a stage on the tile rows (dims 1..) that
-            # no owned cell depends on; what they leave behind is garbage
-            if s > 1:
-              for d, (lo, hi) in enumerate(node.need):
-                ok &= (cell[d + 1] >= lo) & (cell[d + 1] < hi)
             results.append(np.where(ok, mine, GARBAGE))
           if node.hist_oldest is not None:
             slot = (i - node.delay) % sched.period

@@ -23,7 +23,9 @@ def _inputs(orc, dims, seed):
       scale = rng.choice([1e-6, 1e-3, 1.0, 300.0, 3e4], size=shape)
       arrays.append(((rng.random(shape) - 0.3) * scale).astype(dtype))
     else:
-      arrays.append(rng.integers(-40000, 40000, size=shape).astype(dtype))
+      # sums stay below binary16's 65504: float -> int of an infinity is
+      # undefined in C++ (x86 gives INT_MIN, the GPU saturates)
+      arrays.append(rng.integers(-15000, 15000, size=shape).astype(dtype))
   return arrays
 
 

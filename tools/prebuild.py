@@ -84,6 +84,9 @@ def main():
     import test_sharded_run_gpu
     for name, iterate, _ in test_sharded_run_gpu.CASES:
       jobs.append((name, iterate, {}))
+    import test_sanitizer_gpu
+    for name, iterate, _, _ in test_sanitizer_gpu.CASES:
+      jobs.append((name, iterate, {}))
     import half_programs
     for name, _, options in half_programs.CASES:
       jobs.append((name, half_programs.stencil_of(name), options))
