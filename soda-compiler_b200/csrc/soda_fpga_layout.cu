@@ -10,6 +10,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "soda_fpga_layout.h"
 
 namespace {
@@ -30,17 +32,17 @@ struct Row {
 };
 
 template <bool kPack>
-__device__ __forceinline__ Row decode_row(const soda_fpga_layout_t& a) {
+__device__ __forceinline__ Row decode_row(const soda_fpga_layout_t& a,
+                                          long long row, int tile) {
   const int last = a.dim - 1;
-  // this block's tile: dimension 0 of the tile index is the fastest
+  // the tile: dimension 0 of the tile index is the fastest
   int tile_index[3] = {0, 0, 0};
-  int rest = blockIdx.y;
+  int rest = tile;
   const long long tile_linear = rest;
   int extent0 = 0;
   bool inside = true;
   long long original = 0, pitch = 1, row_offset = 0, in_tile_pitch = 1;
-  // in-tile coordinates of this row in dimensions 1..last
-  long long row = blockIdx.x;
+  // (`row`: in-tile coordinates of the row in dimensions 1..last)
   for (int d = 0; d <= last; ++d) {
     int extent = a.dims[d];
     if (d < last) {
@@ -95,7 +97,7 @@ template <typename T, bool kPack, int kBanks>
 __global__ void __launch_bounds__(256)
 wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
             const __grid_constant__ Banks banks) {
-  const Row r = decode_row<kPack>(a);
+  const Row r = decode_row<kPack>(a, blockIdx.x, blockIdx.y);
   if (!r.inside) return;
   T* const row_dense = dense + r.original;
   T* bank[kBanks];
@@ -118,99 +120,133 @@ wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
   }
 }
 
-// ---- staged variant (SODA_FPGA_STAGED=1; not measured yet) -------------------
+// ---- staged variant: one WARP per tile row ------------------------------------
 //
-// The same row goes through shared memory so that BOTH global sides use
-// 16-byte accesses: the dense run and each bank's run are contiguous but
-// start at unrelated alignments, so each side is walked in vectors aligned to
-// ITS address (a peeled head and tail move element-wise) and the shared copy
-// is indexed element-wise in between.
+// The row goes through shared memory so that BOTH global sides use 16-byte
+// accesses: the dense run and each bank's run are contiguous but start at
+// unrelated alignments, so each side is walked in vectors aligned to ITS
+// address (a peeled head and tail move element-wise) and the shared copy is
+// indexed element-wise in between.  A warp owns a row buffer and walks several
+// rows: no block barrier, and the loads of a row are all in flight before the
+// first one is used.  (A first version staged one row per 256-thread BLOCK
+// with a barrier between the two sides: 1981 / 1853 GB/s, no better than the
+// element-wise kernel above, capture r2d — the rows are 4 KB, far too little
+// per barrier.)
 template <typename T>
 struct alignas(16) Vec16 {
   T v[16 / sizeof(T)];
 };
 
+constexpr int kWireWarps = 8;       // warps per block
+constexpr int kWireUnroll = 4;      // vectors a lane has in flight
+
 // Contiguous run of `n` elements between global memory `g` and `n` shared
 // elements reached through `at(j)` (j = 0..n-1), 16 bytes at a time where the
-// global address allows.  kToShared: global -> shared, else shared -> global.
+// global address allows, by the 32 lanes of a warp.  kToShared: global ->
+// shared, else shared -> global.
 template <typename T, bool kToShared, typename At>
-__device__ __forceinline__ void move_run(T* g, int n, At at) {
+__device__ __forceinline__ void move_run(T* g, int n, At at, int lane) {
   constexpr int W = 16 / sizeof(T);
   const int phase = static_cast<int>(
       (reinterpret_cast<uintptr_t>(g) & 15) / sizeof(T));
-  // vector v covers run elements [v * W - phase, v * W - phase + W)
+  // vector v covers run elements [v * W - phase, v * W - phase + W): vector
+  // 0 may start before the run, the last may end after it
   const int vectors = (n + phase + W - 1) / W;
-  for (int v = threadIdx.x; v < vectors; v += blockDim.x) {
-    const int first = v * W - phase;
-    if (first >= 0 && first + W <= n) {
-      Vec16<T>* const wide = reinterpret_cast<Vec16<T>*>(g + first);
-      Vec16<T> pack;
-      if (kToShared) {
-        pack = *wide;
+  for (int v0 = lane; v0 < vectors; v0 += 32 * kWireUnroll) {
+    Vec16<T> pack[kWireUnroll];
+    if (kToShared) {
 #pragma unroll
-        for (int k = 0; k < W; ++k) *at(first + k) = pack.v[k];
-      } else {
-#pragma unroll
-        for (int k = 0; k < W; ++k) pack.v[k] = *at(first + k);
-        *wide = pack;
+      for (int u = 0; u < kWireUnroll; ++u) {
+        const int first = (v0 + 32 * u) * W - phase;
+        if (v0 + 32 * u < vectors && first >= 0 && first + W <= n)
+          pack[u] = *reinterpret_cast<const Vec16<T>*>(g + first);
       }
-    } else {
-      for (int k = 0; k < W; ++k) {
-        const int j = first + k;
-        if (j < 0 || j >= n) continue;
-        if (kToShared)
-          *at(j) = g[j];
-        else
-          g[j] = *at(j);
+    }
+#pragma unroll
+    for (int u = 0; u < kWireUnroll; ++u) {
+      const int v = v0 + 32 * u;
+      if (v >= vectors) break;
+      const int first = v * W - phase;
+      if (first >= 0 && first + W <= n) {
+        if (kToShared) {
+#pragma unroll
+          for (int k = 0; k < W; ++k) *at(first + k) = pack[u].v[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < W; ++k) pack[u].v[k] = *at(first + k);
+          *reinterpret_cast<Vec16<T>*>(g + first) = pack[u];
+        }
+      } else {
+        for (int k = 0; k < W; ++k) {
+          const int j = first + k;
+          if (j < 0 || j >= n) continue;
+          if (kToShared)
+            *at(j) = g[j];
+          else
+            g[j] = *at(j);
+        }
       }
     }
   }
 }
 
 template <typename T, bool kPack, int kBanks>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kWireWarps)
 wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
-                   const __grid_constant__ Banks banks) {
+                   const __grid_constant__ Banks banks, long long rows) {
   extern __shared__ __align__(16) unsigned char staged_raw[];
-  T* const buf = reinterpret_cast<T*>(staged_raw);   // buf[i - i_lo]
-  const Row r = decode_row<kPack>(a);
-  if (!r.inside || r.i_hi <= r.i_lo) return;          // whole block: no barrier
-  const int n = r.i_hi - r.i_lo;
-  T* const row_dense = dense + r.original + r.i_lo;
-  if (kPack)
-    move_run<T, true>(row_dense, n, [&](int j) { return buf + j; });
-  if (!kPack) {
-    // nothing to do yet: the banks are read below
-  }
-  if (kPack) __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pitch = (a.tile_size[0] + 15) & ~15;       // elements per buffer
+  T* const buf = reinterpret_cast<T*>(staged_raw) + warp * pitch;
+  for (long long row = static_cast<long long>(blockIdx.x) * kWireWarps + warp;
+       row < rows; row += static_cast<long long>(gridDim.x) * kWireWarps) {
+    const Row r = decode_row<kPack>(a, row, blockIdx.y);
+    if (!r.inside || r.i_hi <= r.i_lo) continue;       // the whole warp
+    const int n = r.i_hi - r.i_lo;
+    T* const row_dense = dense + r.original + r.i_lo;
+    if (kPack) {
+      move_run<T, true>(row_dense, n, [&](int j) { return buf + j; }, lane);
+      __syncwarp();
+    }
 #pragma unroll
-  for (int b = 0; b < kBanks; ++b) {
-    // cells of this row whose stream element lands in bank slot b
-    const long long first_o = r.stream + r.i_lo;
-    const int skip = static_cast<int>(((b - first_o) % kBanks + kBanks) % kBanks);
-    if (skip >= n) continue;
-    const int count = (n - skip + kBanks - 1) / kBanks;
-    T* const run = static_cast<T*>(banks.ptr[a.bank_vec[b]]) +
-                   (first_o + skip) / kBanks;
-    auto at = [&](int j) { return buf + skip + j * kBanks; };
-    if (kPack)
-      move_run<T, false>(run, count, at);
-    else
-      move_run<T, true>(run, count, at);
-  }
-  if (!kPack) {
-    __syncthreads();
-    move_run<T, false>(row_dense, n, [&](int j) { return buf + j; });
+    for (int b = 0; b < kBanks; ++b) {
+      // cells of this row whose stream element lands in bank slot b
+      const long long first_o = r.stream + r.i_lo;
+      const int skip =
+          static_cast<int>(((b - first_o) % kBanks + kBanks) % kBanks);
+      if (skip >= n) continue;
+      const int count = (n - skip + kBanks - 1) / kBanks;
+      T* const run = static_cast<T*>(banks.ptr[a.bank_vec[b]]) +
+                     (first_o + skip) / kBanks;
+      auto at = [&](int j) { return buf + skip + j * kBanks; };
+      if (kPack)
+        move_run<T, false>(run, count, at, lane);
+      else
+        move_run<T, true>(run, count, at, lane);
+    }
+    __syncwarp();
+    if (!kPack)
+      move_run<T, false>(row_dense, n, [&](int j) { return buf + j; }, lane);
+    __syncwarp();       // the buffer is reused by this warp's next row
   }
 }
 
 template <typename T, bool kPack>
 int launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
            dim3 grid, cudaStream_t s) {
-  // staged variant: a tile row (plus nothing else) in shared memory
-  const size_t smem = static_cast<size_t>(a.tile_size[0]) * sizeof(T) + 16;
+  // staged variant: one row buffer per warp.  SODA_FPGA_STAGED=0 / 1 picks
+  // the element-wise / the staged kernel (default: staged where a row is long
+  // enough for vectors to matter).
+  const size_t pitch = (static_cast<size_t>(a.tile_size[0]) + 15) & ~size_t(15);
+  const size_t smem = pitch * sizeof(T) * kWireWarps;
   const char* env = getenv("SODA_FPGA_STAGED");
-  const bool staged = env != nullptr && env[0] == '1' && smem <= 200 * 1024;
+  bool staged = a.tile_size[0] * sizeof(T) >= 512;
+  if (env != nullptr && (env[0] == '0' || env[0] == '1')) staged = env[0] == '1';
+  staged = staged && smem <= 200 * 1024;
+  const long long rows = grid.x;
+  // enough blocks for every SM to hold its fill, each warp walking ~4 rows
+  const long long wanted = (rows + kWireWarps * 4 - 1) / (kWireWarps * 4);
+  dim3 sgrid(static_cast<unsigned>(std::max<long long>(1, wanted)), grid.y);
 #define SODA_WIRE_LAUNCH(kBanks)                                              \
   if (staged) {                                                               \
     auto fn = wire_kernel_staged<T, kPack, kBanks>;                           \
@@ -218,7 +254,7 @@ int launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                              static_cast<int>(smem)) != cudaSuccess)          \
       return kLaunchFailed;                                                   \
-    fn<<<grid, 256, smem, s>>>(a, dense, table);                              \
+    fn<<<sgrid, 32 * kWireWarps, smem, s>>>(a, dense, table, rows);           \
   } else {                                                                    \
     wire_kernel<T, kPack, kBanks><<<grid, 256, 0, s>>>(a, dense, table);      \
   }

@@ -86,7 +86,8 @@ def add_arguments(parser):
       '--cuda-inline', type=int, dest='cuda_inline', metavar='0|1',
       help='splice every local that is read exactly once into its reader '
       'instead of keeping it in registers between the step that computes it '
-      'and the step that uses it (default: when that holds fewer registers)')
+      'and the step that uses it (bit-identical; default 0: measured no '
+      'faster)')
   parser.add_argument(
       '--cuda-fast', action='store_true', dest='cuda_fast',
       help='emit the kernels for the non-exact build (FMA contraction, '
@@ -117,8 +118,7 @@ class Options:
     self.paired = None if paired is None else bool(paired)
     self.min_blocks = min_blocks
     self.groups = groups
-    # splice locals that are read once into their reader (None: when that
-    # lowers the registers held across steps)
+    # splice locals that are read once into their reader (default: no)
     self.inline = None if inline is None else bool(inline)
 
   @classmethod
@@ -352,37 +352,21 @@ def make_schedules(program, options=None):
   """The kernel variants to compile: the main temporal depth and, when it does
   not divide ``iterate``, the depth of the remainder.
 
-  With ``options.inline`` unset the program is scheduled twice, as written and
-  with its single-use locals spliced into their readers
-  (plan.inline_single_use), and the variant that keeps fewer registers alive
-  across steps wins (a schedule carries the program it was made for:
-  ``sched.program``)."""
+  ``options.inline``: schedule the program with its single-use locals spliced
+  into their readers (plan.inline_single_use; a schedule carries the program
+  it was made for, ``sched.program``).  Off unless asked for: bit-identical
+  and fewer registers held across steps, but measured no faster where it
+  applies (capture r2d: denoise2d 268 vs 270 GCell/s, denoise3d 110 vs 113,
+  sobel2d 1272 vs 1410 — the spliced 16-bit locals need an explicit narrowing
+  that lazy truncation avoids)."""
   options = options or Options()
   check_supported(program)
   if options.is_default():
     found = tuned_mod.lookup(program)     # soda.cuda_tune's winner, if any
     if found:
       options = Options(**found)
-  spliced = (plan_mod.inline_single_use(program) if options.inline is not False
-             else None)
-  if spliced is None:
-    return _make_schedules(program, options)
-  if options.inline:
-    return _make_schedules(spliced, options)
-  try:
-    with_splice = _make_schedules(spliced, options)
-  except util.SemanticError:
-    return _make_schedules(program, options)
-  plain = _make_schedules(program, options)
-  # registers held across steps per vector of cells; on a tie the program as
-  # written wins (splicing an 8/16-bit integer local puts an explicit
-  # narrowing where lazy truncation needed none: sobel2d 22.9 -> 24.8
-  # instructions per cell)
-  cost = lambda schedules: (
-      [s.style != 'reg' for s in schedules],
-      sum(history_registers(s) // s.vecs_per_thread for s in schedules
-          if s.style == 'reg'))
-  return with_splice if cost(with_splice) < cost(plain) else plain
+  spliced = plan_mod.inline_single_use(program) if options.inline else None
+  return _make_schedules(spliced or program, options)
 
 
 def _make_schedules(program, options):

@@ -60,7 +60,7 @@ class Layout:
       depth = self.in_depth if node.is_input else node.ring_depth
       self.ring_depth[node.index] = depth
       self.ring_offset[node.index] = offset
-      ring = depth * sched.plane_elems * node.elem_size
+      ring = depth * sched.ring_pitch * node.elem_size
       offset += -(-ring // 128) * 128
     offset += self.guard
     self.bar_offset = offset
@@ -161,6 +161,9 @@ class _Emitter:
     self.U = sched.period
     self.P = sched.prefetch
     self.PLANE = sched.plane_elems
+    # ring slots are `ring_pitch` elements apart: a plane plus a gap no one
+    # writes, where neighbour reads that leave the plane land (see plan)
+    self.PITCH = sched.ring_pitch
     self.flat = sched.sdim == 1          # 2-D program: registers only
     self.DIN = self.lay.in_depth
 
@@ -531,7 +534,7 @@ class _Emitter:
     for node in lay.loaded_inputs:
       coords = ['org%d' % d for d in range(s)] + ['base + (%s)' % rel_code]
       p.println('soda::tma_load(ring_%s + %d, &a.in_map[%d], bar, %s);' % (
-          node.ident, slot * self.PLANE, node.input_index, ', '.join(coords)))
+          node.ident, slot * self.PITCH, node.input_index, ', '.join(coords)))
 
   def plain_load(self, rel_code, slot):
     p, lay, s, V = self.p, self.lay, self.s, self.V
@@ -562,7 +565,7 @@ class _Emitter:
                 'src[k] : %s(0);' % node.c_type)
       p.un_scope()
       p.println('soda::st_pack<%s, %d>(ring_%s + %d + pos[j], t);' % (
-          node.c_type, V, node.ident, slot * self.PLANE))
+          node.c_type, V, node.ident, slot * self.PITCH))
       p.un_scope()
 
   def emit_tma_prologue(self):
@@ -624,7 +627,7 @@ class _Emitter:
           p.println('%s t[%d];' % (node.c_type, V))
           p.println('soda::ld_pack<%s, %d>(t, ring_%s + %d + pos[j]);' % (
               node.c_type, V, node.ident,
-              self.ring_slot(node, 0, phase) * self.PLANE))
+              self.ring_slot(node, 0, phase) * self.PITCH))
           p.println('#pragma unroll')
           p.println('for (int k = 0; k < %d; ++k) %s[j][k] = t[k];' % (
               V, self.hist(node, phase, 0)))
@@ -632,7 +635,7 @@ class _Emitter:
         else:
           p.println('  soda::ld_pack<%s, %d>(%s[j], ring_%s + %d + pos[j]);'
                     % (node.c_type, V, self.hist(node, phase, 0), node.ident,
-                       self.ring_slot(node, 0, phase) * self.PLANE))
+                       self.ring_slot(node, 0, phase) * self.PITCH))
     self.shuffled = {}     # (node index, age, element) -> variable, this step
     for node in sched.stage_nodes:
       self.emit_stage(node, phase)
@@ -704,7 +707,7 @@ class _Emitter:
       age = node.delay - rest[s - 1]
       p.println('const %s* const s%d = ring_%s + pos[j] + (%d);' % (
           parent.c_type, g, parent.ident,
-          self.ring_slot(parent, age, phase) * self.PLANE + inplane))
+          self.ring_slot(parent, age, phase) * self.PITCH + inplane))
       p.println('%s w%d[%d];' % (parent.c_type, g, V + xhi - xlo))
       inside = [c for c in used if 0 <= c < V]
       if len(inside) >= 2 and xlo <= 0 <= xhi:
@@ -767,7 +770,7 @@ class _Emitter:
                   '%s[k]);' % (V, node.c_type, target))
       p.println('soda::st_pack<%s, %d>(ring_%s + %d + pos[j], %s);' % (
           node.c_type, V, node.ident,
-          self.ring_slot(node, node.delay, phase) * self.PLANE, plane))
+          self.ring_slot(node, node.delay, phase) * self.PITCH, plane))
     if node.output_index is not None and sched.paired:
       # lane A's result (iteration depth/2 - 1) feeds lane B one step later
       feeds = sched.inputs[node.output_index]

@@ -798,6 +798,16 @@ class RegSchedule(Schedule):
     reach = [abs(self.plane_offset(off)) for node in self.stage_nodes
              for _, off in node.loads if self.via_smem(off)]
     self.guard_elems = max(reach) if reach else 0
+    # Planes of a shared ring sit `ring_pitch` elements apart: a neighbour
+    # read that leaves its plane (a halo row's y - 1 or y + 1: garbage that
+    # only feeds garbage) lands in the gap between two planes, which nobody
+    # writes, instead of in the next slot, which another warp may be writing
+    # in the same step — harmless either way, but only this way is the
+    # kernel free of shared-memory races (compute-sanitizer racecheck,
+    # tests/test_sanitizer_gpu.py).  Whole 128-element units keep every slot
+    # aligned for TMA.
+    self.ring_gap = -(-self.guard_elems // 128) * 128
+    self.ring_pitch = self.plane_elems + self.ring_gap
 
   def describe(self):
     lines = ['%sregister-streaming schedule %s: depth %d, tile %s x %d/block, '

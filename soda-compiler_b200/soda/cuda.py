@@ -123,7 +123,10 @@ def build(stencil, build_dir=None, options=None, fast_math=False,
   digest = hashlib.sha256()
   for text in (kernel_src, host_src, str(fast_math)):
     digest.update(text.encode())
-  for name in sorted(os.listdir(CSRC_DIR)) + ['../../include/soda_cuda.h']:
+  # what a program library is compiled from besides its generated files (the
+  # wire-format kernels in csrc/ are a library of their own)
+  for name in ('soda_cuda_device.cuh', 'soda_cuda_runtime.cu',
+               'soda_cuda_runtime.h', '../../include/soda_cuda.h'):
     with open(os.path.join(CSRC_DIR, name), 'rb') as handle:
       digest.update(handle.read())
   out_dir = os.path.join(build_dir or DEFAULT_BUILD_DIR, '%s-%s' % (

@@ -55,6 +55,8 @@ def run_schedule(sched, dims, chunk_rows, final=True):
   n_tiles = [-(-dims[d] // sched.own[d]) for d in range(s)]
   n_chunks = -(-dims[s] // chunk_rows)
   guard = sched.guard_elems
+  pitch = sched.ring_pitch      # slot stride: a plane plus an unwritten gap
+  assert pitch >= plane + guard or not guard
   trip = (sched.flat_box if s == 1 else sched.trip) or 1
   pos = np.arange(plane)
   cell, rest = [], pos
@@ -93,7 +95,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
                   if n.hist_oldest is not None}     # plane a slot holds
       rings = {n.index: [np.full(
           guard + max(n.ring_depth, max([m.ring_depth for m in sched.inputs] +
-                                        [1]) if n.is_input else 0) * plane +
+                                        [1]) if n.is_input else 0) * pitch +
           guard, GARBAGE, dtype=np.int64) for _ in range(lanes)]
                for n in sched.nodes if n.ring_depth and s > 1}
       fb = {k: np.full(plane, GARBAGE, dtype=np.int64) for k in feeds}
@@ -115,7 +117,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
             while issued[node.index] < i + sched.prefetch:
               issued[node.index] += 1
               slot = issued[node.index] % in_depth
-              start = guard + slot * plane
+              start = guard + slot * pitch
               rings[node.index][0][start:start + plane] = input_plane(
                   node, issued[node.index])
           if node.hist_oldest is None:
@@ -146,7 +148,12 @@ def run_schedule(sched, dims, chunk_rows, final=True):
                   assert parent.delay + 1 <= age <= parent.delay + depth - 1, (
                       node.ident, parent.ident, age, 'ring timing')
                 slot = (i - age) % depth
-                addr = guard + slot * plane + pos + sched.plane_offset(off)
+                addr = guard + slot * pitch + pos + sched.plane_offset(off)
+                # a read that leaves the plane lands in the gap, never in a
+                # slot another warp may be writing in this step
+                rel = addr - guard - slot * pitch
+                assert ((rel >= plane - pitch) & (rel < pitch)).all(), (
+                    node.ident, parent.ident, 'read reaches another slot')
                 got = rings[parent.index][lane][addr]
               else:
                 assert parent.hist_oldest is not None
@@ -207,7 +214,7 @@ def run_schedule(sched, dims, chunk_rows, final=True):
         # one barrier per step: ring planes become visible to the next step
         for node, results in ring_writes:
           slot = (i - node.delay) % node.ring_depth
-          start = guard + slot * plane
+          start = guard + slot * pitch
           for lane in range(lanes):
             rings[node.index][lane][start:start + plane] = results[lane]
         fb.update(new_fb)

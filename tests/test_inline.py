@@ -8,7 +8,7 @@ program with tests/program_eval.py (periodic boundaries, every cell defined)
 a narrowing integer local, a chain of single-use locals, a local read once
 at a non-zero offset.  The schedules of spliced programs run through the same
 CPU schedule models as any other (tests/test_plan.py style) below; GPU
-parity of every benchmark runs on the spliced kernels by default.
+parity of spliced kernels: the `inline` cases of tests/test_parity_gpu.py.
 """
 import numpy as np
 import pytest
@@ -119,10 +119,11 @@ def test_spliced_schedules_run_on_the_cpu_models(name, monkeypatch):
       runner.check_outputs(sched, dims, outs)
 
 
-def test_default_choice_holds_fewer_registers(monkeypatch):
+def test_splicing_is_on_request_and_holds_fewer_registers(monkeypatch):
   monkeypatch.setenv('SODA_CUDA_TUNED', '0')
   program = plan.extract_program(common.stencil('denoise2d'))
-  plain = codegen.make_schedules(program, codegen.Options(inline=False))[0]
-  auto = codegen.make_schedules(program)[0]
-  assert len(auto.program.stages) == 2
-  assert codegen.history_registers(auto) < codegen.history_registers(plain)
+  plain = codegen.make_schedules(program)[0]
+  assert len(plain.program.stages) == len(program.stages)    # default: as written
+  spliced = codegen.make_schedules(program, codegen.Options(inline=True))[0]
+  assert len(spliced.program.stages) == 2
+  assert codegen.history_registers(spliced) < codegen.history_registers(plain)

@@ -56,6 +56,12 @@ CASES = [
     ('blur', 1, (2048, 128), {'style': 'ring'}),
     ('heat3d', 2, (192, 48, 33), {'style': 'ring'}),
     ('heat3d', 2, (256, 64, 40), {'tile': [128, 16], 'threads': 256}),
+    # single-use locals spliced into their readers (--cuda-inline 1)
+    ('denoise2d', 1, (777, 141), {'inline': 1}),
+    ('denoise3d', 1, (93, 41, 37), {'inline': 1}),
+    ('denoise3d', 1, (128, 48, 24), {'inline': 1, 'tile': [128, 32],
+                                     'threads': 512, 'prefetch': 1}),
+    ('sobel2d', 1, (1101, 157), {'inline': 1}),
 ]
 
 
