@@ -697,6 +697,13 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
   Lane* lane = nullptr;
   int rc = current_lane(&lane);
   if (rc != kSuccess) return rc;
+  if (g_last_lane != lane || g_stats_aggregate) {
+    // callers that drive single launches (the slab runner) read the kernel
+    // configuration of their last launch from the same place as a run's
+    std::lock_guard<std::mutex> lock(g_mutex);
+    g_last_lane = lane;
+    g_stats_aggregate = false;
+  }
   return launch_on(lane, prog, depth, inputs, outputs, dims, row_begin,
                    row_end, valid_lo, valid_hi, stream, forced_chunk_rows);
 }
