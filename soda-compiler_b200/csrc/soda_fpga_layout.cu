@@ -11,6 +11,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "soda_fpga_layout.h"
 
@@ -122,69 +123,129 @@ wire_kernel(const __grid_constant__ soda_fpga_layout_t a, T* dense,
 
 // ---- staged variant: one WARP per tile row ------------------------------------
 //
-// The row goes through shared memory so that BOTH global sides use 16-byte
-// accesses: the dense run and each bank's run are contiguous but start at
-// unrelated alignments, so each side is walked in vectors aligned to ITS
-// address (a peeled head and tail move element-wise) and the shared copy is
-// indexed element-wise in between.  A warp owns a row buffer and walks several
-// rows: no block barrier, and the loads of a row are all in flight before the
-// first one is used.  (A first version staged one row per 256-thread BLOCK
-// with a barrier between the two sides: 1981 / 1853 GB/s, no better than the
-// element-wise kernel above, capture r2d — the rows are 4 KB, far too little
-// per barrier.)
+// A tile row is one contiguous run of the dense array and one contiguous run
+// in every bank (the stream interleaves the banks element by element), all
+// at unrelated alignments.  A warp owns a shared-memory copy of the row and
+// walks several rows; no block barrier.
+//   dense side   16-byte global accesses aligned to the dense address, and —
+//                the copy is laid out at the same phase — 16-byte shared
+//                accesses (conflict-free);
+//   bank side    4/8-byte global accesses, consecutive lanes on consecutive
+//                words (coalesced), element-wise shared accesses with a stride
+//                of `kBanks` elements (conflict-free for 16-bit elements in
+//                two banks);
+// with the loads of a row in flight together before the first is used.
+// History (profiles/README.md): element-wise kernel 2258 / 1878 GB/s; a row per
+// 256-thread block with a barrier between the sides 1981 / 1853; a row per
+// warp with 16-byte accesses on both global sides but element-wise shared
+// accesses 2583 / 2305 (shared-memory bank conflicts: ~770 wavefronts per
+// 4 KB row).
 template <typename T>
 struct alignas(16) Vec16 {
   T v[16 / sizeof(T)];
 };
 
 constexpr int kWireWarps = 8;       // warps per block
-constexpr int kWireUnroll = 4;      // vectors a lane has in flight
+constexpr int kWireUnroll = 4;      // accesses a lane has in flight
 
-// Contiguous run of `n` elements between global memory `g` and `n` shared
-// elements reached through `at(j)` (j = 0..n-1), 16 bytes at a time where the
-// global address allows, by the 32 lanes of a warp.  kToShared: global ->
-// shared, else shared -> global.
-template <typename T, bool kToShared, typename At>
-__device__ __forceinline__ void move_run(T* g, int n, At at, int lane) {
+// Dense run g[0..n) <-> shared copy buf[phase + j], phase = misalignment of g
+// in elements (so both sides of a full vector are 16-byte aligned).
+template <typename T, bool kToShared>
+__device__ __forceinline__ void move_dense(T* g, int n, T* buf, int phase,
+                                           int lane) {
   constexpr int W = 16 / sizeof(T);
-  const int phase = static_cast<int>(
-      (reinterpret_cast<uintptr_t>(g) & 15) / sizeof(T));
-  // vector v covers run elements [v * W - phase, v * W - phase + W): vector
-  // 0 may start before the run, the last may end after it
+  // vector v covers run elements [v * W - phase, v * W - phase + W)
   const int vectors = (n + phase + W - 1) / W;
   for (int v0 = lane; v0 < vectors; v0 += 32 * kWireUnroll) {
     Vec16<T> pack[kWireUnroll];
-    if (kToShared) {
+    bool whole[kWireUnroll];
 #pragma unroll
-      for (int u = 0; u < kWireUnroll; ++u) {
-        const int first = (v0 + 32 * u) * W - phase;
-        if (v0 + 32 * u < vectors && first >= 0 && first + W <= n)
-          pack[u] = *reinterpret_cast<const Vec16<T>*>(g + first);
-      }
+    for (int u = 0; u < kWireUnroll; ++u) {
+      const int first = (v0 + 32 * u) * W - phase;
+      whole[u] = v0 + 32 * u < vectors && first >= 0 && first + W <= n;
+      if (whole[u])
+        pack[u] = kToShared
+                      ? *reinterpret_cast<const Vec16<T>*>(g + first)
+                      : *reinterpret_cast<const Vec16<T>*>(buf + first + phase);
     }
 #pragma unroll
     for (int u = 0; u < kWireUnroll; ++u) {
       const int v = v0 + 32 * u;
       if (v >= vectors) break;
       const int first = v * W - phase;
-      if (first >= 0 && first + W <= n) {
-        if (kToShared) {
-#pragma unroll
-          for (int k = 0; k < W; ++k) *at(first + k) = pack[u].v[k];
-        } else {
-#pragma unroll
-          for (int k = 0; k < W; ++k) pack[u].v[k] = *at(first + k);
+      if (whole[u]) {
+        if (kToShared)
+          *reinterpret_cast<Vec16<T>*>(buf + first + phase) = pack[u];
+        else
           *reinterpret_cast<Vec16<T>*>(g + first) = pack[u];
-        }
-      } else {
+      } else {      // head or tail of the run
         for (int k = 0; k < W; ++k) {
           const int j = first + k;
           if (j < 0 || j >= n) continue;
           if (kToShared)
-            *at(j) = g[j];
+            buf[j + phase] = g[j];
           else
-            g[j] = *at(j);
+            g[j] = buf[j + phase];
         }
+      }
+    }
+  }
+}
+
+// Bank run g[0..count) <-> shared elements sm[e * stride], one 4- or 8-byte
+// word of the run per lane and access (the head and tail that do not fill an aligned word
+// move element-wise).
+template <typename T, bool kToShared>
+__device__ __forceinline__ void move_strided(T* g, int count, T* sm, int stride,
+                                             int lane) {
+  // measured (capture r2j, blur 32768^2 u16, two banks): loads want 8-byte
+  // words (unpack 4015 -> 4290 GB/s), stores 4-byte ones (pack 5642 vs 4938)
+  constexpr int kWordBytes = (kToShared || sizeof(T) == 8) ? 8 : 4;
+  constexpr int N = kWordBytes / static_cast<int>(sizeof(T));
+  using Word = typename std::conditional<kWordBytes == 8, uint64_t,
+                                         uint32_t>::type;
+  union Cells {
+    Word word;
+    T cell[N];
+  };
+  const int misaligned = static_cast<int>(
+      (reinterpret_cast<uintptr_t>(g) & (sizeof(Word) - 1)) / sizeof(T));
+  const int head = min(count, (N - misaligned) % N);
+  const int words = (count - head) / N;
+  const int tail = count - head - words * N;
+  if (lane < head) {
+    if (kToShared) sm[lane * stride] = g[lane];
+    else g[lane] = sm[lane * stride];
+  }
+  if (lane < tail) {
+    const int e = head + words * N + lane;
+    if (kToShared) sm[e * stride] = g[e];
+    else g[e] = sm[e * stride];
+  }
+  Word* const body = reinterpret_cast<Word*>(g + head);
+  T* const sm_body = sm + head * stride;
+  // loads: twice as many in flight as on the 16-byte side
+  constexpr int kUnroll = kToShared ? 2 * kWireUnroll : kWireUnroll;
+  for (int w0 = lane; w0 < words; w0 += 32 * kUnroll) {
+    Cells cells[kUnroll];
+    if (kToShared) {
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        if (w0 + 32 * u < words) cells[u].word = body[w0 + 32 * u];
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int w = w0 + 32 * u;
+      if (w >= words) break;
+      if (kToShared) {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          sm_body[(w * N + k) * stride] = cells[u].cell[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < N; ++k)
+          cells[u].cell[k] = sm_body[(w * N + k) * stride];
+        body[w] = cells[u].word;
       }
     }
   }
@@ -195,8 +256,10 @@ __global__ void __launch_bounds__(32 * kWireWarps)
 wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
                    const __grid_constant__ Banks banks, long long rows) {
   extern __shared__ __align__(16) unsigned char staged_raw[];
+  constexpr int W = 16 / sizeof(T);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pitch = (a.tile_size[0] + 15) & ~15;       // elements per buffer
+  // elements per row buffer: the row, its phase, rounded to whole vectors
+  const int pitch = (a.tile_size[0] + 2 * W + W - 1) / W * W;
   T* const buf = reinterpret_cast<T*>(staged_raw) + warp * pitch;
   for (long long row = static_cast<long long>(blockIdx.x) * kWireWarps + warp;
        row < rows; row += static_cast<long long>(gridDim.x) * kWireWarps) {
@@ -204,8 +267,10 @@ wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
     if (!r.inside || r.i_hi <= r.i_lo) continue;       // the whole warp
     const int n = r.i_hi - r.i_lo;
     T* const row_dense = dense + r.original + r.i_lo;
+    const int phase = static_cast<int>(
+        (reinterpret_cast<uintptr_t>(row_dense) & 15) / sizeof(T));
     if (kPack) {
-      move_run<T, true>(row_dense, n, [&](int j) { return buf + j; }, lane);
+      move_dense<T, true>(row_dense, n, buf, phase, lane);
       __syncwarp();
     }
 #pragma unroll
@@ -218,15 +283,10 @@ wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
       const int count = (n - skip + kBanks - 1) / kBanks;
       T* const run = static_cast<T*>(banks.ptr[a.bank_vec[b]]) +
                      (first_o + skip) / kBanks;
-      auto at = [&](int j) { return buf + skip + j * kBanks; };
-      if (kPack)
-        move_run<T, false>(run, count, at, lane);
-      else
-        move_run<T, true>(run, count, at, lane);
+      move_strided<T, !kPack>(run, count, buf + phase + skip, kBanks, lane);
     }
     __syncwarp();
-    if (!kPack)
-      move_run<T, false>(row_dense, n, [&](int j) { return buf + j; }, lane);
+    if (!kPack) move_dense<T, false>(row_dense, n, buf, phase, lane);
     __syncwarp();       // the buffer is reused by this warp's next row
   }
 }
@@ -237,7 +297,9 @@ int launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
   // staged variant: one row buffer per warp.  SODA_FPGA_STAGED=0 / 1 picks
   // the element-wise / the staged kernel (default: staged where a row is long
   // enough for vectors to matter).
-  const size_t pitch = (static_cast<size_t>(a.tile_size[0]) + 15) & ~size_t(15);
+  constexpr size_t W = 16 / sizeof(T);
+  const size_t pitch =
+      (static_cast<size_t>(a.tile_size[0]) + 2 * W + W - 1) / W * W;
   const size_t smem = pitch * sizeof(T) * kWireWarps;
   const char* env = getenv("SODA_FPGA_STAGED");
   bool staged = a.tile_size[0] * sizeof(T) >= 512;
