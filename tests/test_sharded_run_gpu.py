@@ -94,3 +94,23 @@ def test_device_list_from_the_environment_and_errors(monkeypatch):
   assert library.slab_stats == []
   with pytest.raises(soda_cuda.CudaError):
     library.run(inputs, devices='0,99')
+
+
+@pytest.mark.parametrize('name,iterate,dims', [
+    ('jacobi2d', 3, (1536, 200)), ('heat3d', 2, (131, 35, 52)),
+    ('blur', 1, (2000, 1000))])
+def test_reference_harness_accepts_a_sharded_run(name, iterate, dims):
+  """The reference's own generated `<app>_test` (unmodified, oracle/_ref/)
+  calls the CUDA library where the FPGA would run; here that one call is
+  spread over three slabs.  Its golden loop finds no mismatch."""
+  import os
+  import ref_harness
+  lib = ref_harness.lib_path(name, iterate)
+  if not os.path.exists(lib):
+    pytest.skip('oracle/_ref was not built (needs /root/reference)')
+  stencil = common.stencil(name, iterate)
+  harness = ref_harness.RefHarness(lib, stencil)
+  library = soda_cuda.compile_stencil(stencil)
+  assert harness.test(
+      dims, lambda inputs: library.run(inputs, devices='0,0,0')) == 0
+  assert len(library.slab_stats) == len(library.shard_plan(dims, 3))
