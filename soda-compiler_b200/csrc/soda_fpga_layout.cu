@@ -252,7 +252,7 @@ __device__ __forceinline__ void move_strided(T* g, int count, T* sm, int stride,
 }
 
 template <typename T, bool kPack, int kBanks>
-__global__ void __launch_bounds__(32 * kWireWarps)
+__global__ void __launch_bounds__(32 * kWireWarps, 4)
 wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
                    const __grid_constant__ Banks banks, long long rows) {
   extern __shared__ __align__(16) unsigned char staged_raw[];

@@ -366,6 +366,14 @@ class _Emitter:
       p.println('const unsigned ok_n%d = static_cast<unsigned>(max(0, min('
                 'mine_hi%d, a.valid_hi[%d][%d] - base + %d) - ok_lo%d));' % (
                     n, n, n, s, lag, n))
+      p.println('// steps whose row this thread stores with one 128-bit store: '
+                'the valid steps if')
+      p.println('// its whole vector is owned and valid, none otherwise (one '
+                'compare per step)')
+      p.println('unsigned fast_n%d[%d];' % (n, self.VPT))
+      p.println('#pragma unroll')
+      p.println('for (int j = 0; j < %d; ++j) fast_n%d[j] = fast%d[j] ? ok_n%d '
+                ': 0u;' % (self.VPT, n, n, n))
       p.println('%s* op%d[%d];   // row of step 0 (dereferenced only inside '
                 'the window)' % (node.c_type, n, self.VPT))
       p.println('#pragma unroll')
@@ -780,7 +788,8 @@ class _Emitter:
     if node.output_index is not None:
       n = node.output_index
       half = '.v.y' if sched.paired else ''
-      p.println('if (row_ok && fast%d[j])' % n)
+      p.println('if (static_cast<unsigned>(ii - ok_lo%d) < fast_n%d[j])' % (
+          n, n))
       p.do_scope()
       p.println('%s o[%d];' % (node.c_type, V))
       p.println('#pragma unroll')

@@ -87,6 +87,9 @@ def main():
     import test_sanitizer_gpu
     for name, iterate, _, _ in test_sanitizer_gpu.CASES:
       jobs.append((name, iterate, {}))
+    import dim4_programs
+    for name, _ in dim4_programs.CASES:
+      jobs.append((name, dim4_programs.stencil_of(name), {}))
     import half_programs
     for name, _, options in half_programs.CASES:
       jobs.append((name, half_programs.stencil_of(name), options))
