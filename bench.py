@@ -24,8 +24,9 @@ What is timed
             the other ranks wait).  `copy_ceiling` is the same bytes moved by
             plain cudaMemcpyAsync in both directions at once with no compute:
             what this machine's host<->device path allows at N devices.
-  extra     BASELINE configs 3, 4 and 5, device-resident, outside
-            ms_per_step: sobel2d / denoise2d 32768^2 (N = 1), heat3d /
+  extra     BASELINE configs 1, 3, 4 and 5, device-resident, outside
+            ms_per_step: blur 2000 x 1000 (launch-bound: one 12 us kernel),
+            sobel2d / denoise2d 32768^2 (N = 1), heat3d /
             jacobi3d 1024^3 x 32 and denoise3d 768^3 x 16 applications cut
             into N slabs (STRONG scaling), each with its recomputed roofline
             fraction; with N > 1 also a small sharded run compared bit for
@@ -218,6 +219,7 @@ def workload_config(n_gpus):
 # for non-exact float builds) is listed NEXT TO the bit-exact one, which is
 # bound by FP32 instruction issue in reference operation order.
 EXTRA_CASES = (
+    ('blur', 1, (2000, 1000), 4, False, 'exact'),      # BASELINE configs[0]
     ('sobel2d', 1, (32768, 32768), 4, False, 'exact'),
     ('denoise2d', 1, (32768, 32768), 12, False, 'exact'),
     ('denoise2d', 1, (32768, 32768), 12, False, 'fast'),
@@ -280,22 +282,25 @@ def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
       for _ in range(2):
         runner.run(iterate)
       times = []
+      cells = float(np.prod(dims))
+      inner = 50 if cells < 1e7 else 1     # microsecond kernels: time a batch
       for _ in range(reps):
         barrier()
         start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
         start.record()
-        runner.run(iterate)
+        for _ in range(inner):
+          runner.run(iterate)
         stop.record()
         torch.cuda.synchronize()
-        times.append(max_over_ranks(start.elapsed_time(stop)))
+        times.append(max_over_ranks(start.elapsed_time(stop)) / inner)
       ms = float(np.median(times))
-      cells = float(np.prod(dims))
       passes = len(runner.plan(iterate))
       achieved = cells * bytes_per_cell * passes / (ms * 1e6)   # GB/s, all GPUs
       entry.update({
           'ms': ms, 'value': cells * iterate / (ms * 1e6), 'unit': 'GCell/s',
           'temporal_depth': runner.plan(iterate)[0], 'passes': passes,
           'launches_rank0': runner.launches_per_run(iterate),
+          'runs_per_timing': inner,
           'roofline': {
               'bound': 'hbm', 'achieved': achieved, 'peak': peak * world,
               'unit': 'GB/s', 'frac': achieved / (peak * world),
