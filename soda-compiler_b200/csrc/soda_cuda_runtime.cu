@@ -887,9 +887,25 @@ int run_pipelined(Lane* lane, const ProgramDesc& prog, buffer_t* const* inputs,
   int loaded = 0;
   int copied = copy_begin;
   pieces = std::max(1, std::min(pieces, rows));
+  // Piece boundaries: equal pieces, the last one cut again into 1/2, 1/4, 1/4.
+  // The host-to-device copies are the critical resource; what follows the
+  // last of them — its launches and the copy back of its rows — is exposed,
+  // so the last piece is small.
+  std::vector<int> bounds;
+  for (int piece = 0; piece < pieces; ++piece)
+    bounds.push_back(static_cast<int>(
+        static_cast<long long>(rows) * (piece + 1) / pieces));
+  if (pieces >= 4) {
+    const int last_begin = bounds[pieces - 2], last = rows - last_begin;
+    if (last >= 64) {
+      bounds.back() = last_begin + last / 2;
+      bounds.push_back(last_begin + last / 2 + last / 4);
+      bounds.push_back(rows);
+    }
+  }
+  pieces = static_cast<int>(bounds.size());
   for (int piece = 0; piece < pieces; ++piece) {
-    const int upto = static_cast<int>(
-        static_cast<long long>(rows) * (piece + 1) / pieces);
+    const int upto = bounds[piece];
     if (upto <= loaded) continue;
     for (int k = 0; k < prog.n_in; ++k) {
       const size_t off =
