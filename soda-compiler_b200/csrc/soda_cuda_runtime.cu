@@ -76,6 +76,24 @@ struct MapEntry {
   CUtensorMap map;
 };
 
+// Pinned bounce buffers for PAGEABLE caller memory.  cudaMemcpyAsync on
+// pageable memory is staged by the driver on one thread (measured 5.8 GB/s
+// each way on this pool's hosts against 50 GB/s from pinned memory, capture
+// r2s) and pinning the caller's arrays for the call costs more than it saves
+// (registering 2 x 1 GiB: 165-280 ms).  Instead the runtime copies through
+// its own pinned slots with a few host threads: slot i + 1 is filled while
+// slot i is on the wire.
+struct Stager {
+  static constexpr int kSlots = 3;
+  size_t slot_bytes = 0;
+  void* slot[kSlots] = {};
+  cudaEvent_t done[kSlots] = {};
+  bool busy[kSlots] = {};        // `done` has been recorded for this slot
+  void* out_dst[kSlots] = {};    // copy-out pending: caller memory, bytes
+  size_t out_bytes[kSlots] = {};
+  int next = 0;
+};
+
 // One execution lane: a device with the streams, events, buffer pool and
 // caches of one stream of calls.  Lane (d, 0) serves callers whose current
 // device is d; a sharded run over devices "0,1,1" also uses lane (1, 1).
@@ -98,6 +116,7 @@ struct Lane {
   std::vector<FnInfo> fns;
   std::vector<ChunkEntry> chunks;
   std::vector<MapEntry> maps;
+  Stager stage_in, stage_out;
 };
 
 std::mutex g_mutex;            // lanes, params, last-run bookkeeping
@@ -295,6 +314,157 @@ struct EventLease {
     for (cudaEvent_t ev : held) lane->idle_events.push_back(ev);
   }
 };
+
+// ---- pageable caller memory ---------------------------------------------------
+
+bool staging_enabled() {
+  const char* v = getenv("SODA_CUDA_STAGING");
+  return v == nullptr || v[0] != '0';
+}
+
+// Is `ptr` ordinary (not pinned, not registered, not managed) host memory?
+bool is_pageable(const void* ptr) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy by a few threads (SODA_CUDA_COPY_THREADS, default half the cores, at
+// most 8): one thread does not saturate the host's memory system.
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+  static const int wanted = [] {
+    if (const char* v = getenv("SODA_CUDA_COPY_THREADS")) return atoi(v);
+    const unsigned cores = std::thread::hardware_concurrency();
+    return static_cast<int>(std::min(8u, std::max(1u, cores / 2)));
+  }();
+  const int parts = static_cast<int>(std::max<size_t>(
+      1, std::min<size_t>(std::max(1, wanted), bytes >> 20)));
+  if (parts == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t each = ((bytes + parts - 1) / parts + 4095) & ~size_t(4095);
+  std::vector<std::thread> helpers;
+  for (int t = 1; t < parts; ++t) {
+    const size_t begin = std::min(bytes, each * t);
+    const size_t end = std::min(bytes, begin + each);
+    if (end > begin)
+      helpers.emplace_back([=] {
+        memcpy(static_cast<char*>(dst) + begin,
+               static_cast<const char*>(src) + begin, end - begin);
+      });
+  }
+  memcpy(dst, src, std::min(bytes, each));
+  for (auto& h : helpers) h.join();
+}
+
+int ensure_stager(Stager* st) {
+  size_t want = size_t(32) << 20;
+  if (const char* v = getenv("SODA_CUDA_STAGE_KB"))
+    want = std::max<size_t>(4096, static_cast<size_t>(atol(v)) << 10);
+  if (st->slot_bytes == want) return kSuccess;
+  for (int k = 0; k < Stager::kSlots; ++k) {
+    if (st->slot[k] != nullptr) {
+      if (st->busy[k]) cudaEventSynchronize(st->done[k]);
+      cudaFreeHost(st->slot[k]);
+      st->slot[k] = nullptr;
+    }
+    st->busy[k] = false;
+    st->out_bytes[k] = 0;
+    if (st->done[k] == nullptr)
+      SODA_CHECK(cudaEventCreateWithFlags(&st->done[k], cudaEventDisableTiming),
+                 kDeviceRunFailed);
+    SODA_CHECK(cudaHostAlloc(&st->slot[k], want, cudaHostAllocDefault),
+               kOutOfMemory);
+  }
+  st->slot_bytes = want;
+  st->next = 0;
+  return kSuccess;
+}
+
+// A slot whose bytes have reached the device (copy-in) or the caller
+// (copy-out) and may be refilled.
+int drain_slot(Stager* st, int k) {
+  if (st->busy[k]) {
+    SODA_CHECK(cudaEventSynchronize(st->done[k]), kDeviceSyncFailed);
+    st->busy[k] = false;
+  }
+  if (st->out_bytes[k] != 0) {
+    parallel_memcpy(st->out_dst[k], st->slot[k], st->out_bytes[k]);
+    st->out_bytes[k] = 0;
+  }
+  return kSuccess;
+}
+
+// Host -> device on `stream`; pageable sources go through the bounce slots.
+int copy_in(Lane* lane, void* dst, const void* src, size_t bytes, bool staged,
+            cudaStream_t stream) {
+  if (!staged) {
+    SODA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream),
+               kCopyToDeviceFailed);
+    return kSuccess;
+  }
+  Stager* st = &lane->stage_in;
+  int rc = ensure_stager(st);
+  if (rc != kSuccess) return rc;
+  for (size_t off = 0; off < bytes; off += st->slot_bytes) {
+    const int k = st->next;
+    st->next = (k + 1) % Stager::kSlots;
+    rc = drain_slot(st, k);
+    if (rc != kSuccess) return rc;
+    const size_t n = std::min(st->slot_bytes, bytes - off);
+    parallel_memcpy(st->slot[k], static_cast<const char*>(src) + off, n);
+    SODA_CHECK(cudaMemcpyAsync(static_cast<char*>(dst) + off, st->slot[k], n,
+                               cudaMemcpyHostToDevice, stream),
+               kCopyToDeviceFailed);
+    SODA_CHECK(cudaEventRecord(st->done[k], stream), kCopyToDeviceFailed);
+    st->busy[k] = true;
+  }
+  return kSuccess;
+}
+
+// Device -> host on `stream`; pageable destinations receive their bytes when
+// the slot is drained (at its next use, or by finish_copies).
+int copy_out(Lane* lane, void* dst, const void* src, size_t bytes, bool staged,
+             cudaStream_t stream) {
+  if (!staged) {
+    SODA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream),
+               kCopyToHostFailed);
+    return kSuccess;
+  }
+  Stager* st = &lane->stage_out;
+  int rc = ensure_stager(st);
+  if (rc != kSuccess) return rc;
+  for (size_t off = 0; off < bytes; off += st->slot_bytes) {
+    const int k = st->next;
+    st->next = (k + 1) % Stager::kSlots;
+    rc = drain_slot(st, k);
+    if (rc != kSuccess) return rc;
+    const size_t n = std::min(st->slot_bytes, bytes - off);
+    SODA_CHECK(cudaMemcpyAsync(st->slot[k], static_cast<const char*>(src) + off,
+                               n, cudaMemcpyDeviceToHost, stream),
+               kCopyToHostFailed);
+    SODA_CHECK(cudaEventRecord(st->done[k], stream), kCopyToHostFailed);
+    st->busy[k] = true;
+    st->out_dst[k] = static_cast<char*>(dst) + off;
+    st->out_bytes[k] = n;
+  }
+  return kSuccess;
+}
+
+// Everything still in a copy-out slot reaches the caller's memory, oldest
+// first.
+int finish_copies(Lane* lane) {
+  Stager* st = &lane->stage_out;
+  for (int step = 0; step < Stager::kSlots; ++step) {
+    const int rc = drain_slot(st, (st->next + step) % Stager::kSlots);
+    if (rc != kSuccess) return rc;
+  }
+  return kSuccess;
+}
 
 const KernelVariant* find_variant(const ProgramDesc& prog, int depth) {
   for (int i = 0; i < prog.n_variants; ++i)
@@ -697,7 +867,7 @@ int launch(const ProgramDesc& prog, int depth, const void* const* inputs,
   Lane* lane = nullptr;
   int rc = current_lane(&lane);
   if (rc != kSuccess) return rc;
-  if (g_last_lane != lane || g_stats_aggregate) {
+  {
     // callers that drive single launches (the slab runner) read the kernel
     // configuration of their last launch from the same place as a run's
     std::lock_guard<std::mutex> lock(g_mutex);
@@ -850,6 +1020,14 @@ int run_pipelined(Lane* lane, const ProgramDesc& prog, buffer_t* const* inputs,
     }
   }
   begin_stats(lane, cells, prog.iterate, depths[0], false);
+  // pageable caller memory goes through pinned bounce buffers (Stager)
+  bool stage_input[kRtMaxTensors] = {}, stage_output[kRtMaxTensors] = {};
+  if (staging_enabled()) {
+    for (int k = 0; k < prog.n_in; ++k)
+      stage_input[k] = is_pageable(inputs[k]->host);
+    for (int k = 0; k < prog.n_out; ++k)
+      stage_output[k] = is_pageable(outputs[k]->host);
+  }
 
   // streamed reach of every launch; rows (local) each launch must produce
   std::vector<int> reach_lo(n_launch), reach_hi(n_launch), hold(n_launch);
@@ -914,10 +1092,9 @@ int run_pipelined(Lane* lane, const ProgramDesc& prog, buffer_t* const* inputs,
                               row_cells * prog.in_elem[k];
       const size_t bytes =
           static_cast<size_t>(upto - loaded) * row_cells * prog.in_elem[k];
-      SODA_CHECK(cudaMemcpyAsync(static_cast<char*>(in_dev[k]) + off,
-                                 inputs[k]->host + host_off, bytes,
-                                 cudaMemcpyHostToDevice, s_in),
-                 kCopyToDeviceFailed);
+      rc = copy_in(lane, static_cast<char*>(in_dev[k]) + off,
+                   inputs[k]->host + host_off, bytes, stage_input[k], s_in);
+      if (rc != kSuccess) return rc;
     }
     loaded = upto;
     cudaEvent_t arrived = events.get();
@@ -970,10 +1147,10 @@ int run_pipelined(Lane* lane, const ProgramDesc& prog, buffer_t* const* inputs,
                                 row_cells * prog.out_elem[k];
         const size_t bytes = static_cast<size_t>(done - copied) * row_cells *
                              prog.out_elem[k];
-        SODA_CHECK(cudaMemcpyAsync(outputs[k]->host + host_off,
-                                   static_cast<char*>(out_dev[k]) + off, bytes,
-                                   cudaMemcpyDeviceToHost, s_out),
-                   kCopyToHostFailed);
+        rc = copy_out(lane, outputs[k]->host + host_off,
+                      static_cast<char*>(out_dev[k]) + off, bytes,
+                      stage_output[k], s_out);
+        if (rc != kSuccess) return rc;
       }
       copied = done;
     }
@@ -985,6 +1162,8 @@ int run_pipelined(Lane* lane, const ProgramDesc& prog, buffer_t* const* inputs,
   SODA_CHECK(cudaStreamSynchronize(s_in), kDeviceSyncFailed);
   SODA_CHECK(cudaStreamSynchronize(s_run), kDeviceSyncFailed);
   SODA_CHECK(cudaStreamSynchronize(s_out), kDeviceSyncFailed);
+  rc = finish_copies(lane);
+  if (rc != kSuccess) return rc;
   lease.completed = true;
   if (copied != copy_end) {
     fprintf(stderr, "ERROR: pipeline finished at row %d of %d\n", copied,
@@ -1092,7 +1271,7 @@ int run_sharded(const ProgramDesc& prog, buffer_t* const* inputs,
   std::vector<Lane*> lanes(n, nullptr);
   std::vector<std::thread> threads;
   int caller_device = 0;
-  cudaGetDevice(&caller_device);
+  SODA_CHECK(cudaGetDevice(&caller_device), kNoDeviceInterface);
   for (int r = 0; r < n; ++r) {
     int replica = 0;
     for (int q = 0; q < r; ++q)
@@ -1284,6 +1463,17 @@ int run_buffers(const ProgramDesc& prog, buffer_t* const* inputs,
   int pieces = static_cast<int>(std::min<size_t>(16, moved >> 27));  // 128 MiB
   if (const char* v = getenv("SODA_CUDA_PIECES")) pieces = atoi(v);
   pieces = std::min(pieces, dims[prog.dim - 1]);
+  // pageable arrays of some size: one piece, but through the bounce buffers
+  // (the driver's own staging of pageable copies runs at a ninth of the link)
+  if (all_host && pieces <= 1 && moved >= (size_t(16) << 20) &&
+      staging_enabled() && getenv("SODA_CUDA_PIECES") == nullptr) {
+    bool pageable = false;
+    for (int k = 0; k < prog.n_in; ++k)
+      pageable = pageable || is_pageable(inputs[k]->host);
+    for (int k = 0; k < prog.n_out; ++k)
+      pageable = pageable || is_pageable(outputs[k]->host);
+    if (pageable) pieces = 2;
+  }
   if (all_host && pieces > 1) {
     const Slab whole = {0, dims[prog.dim - 1], 0, dims[prog.dim - 1]};
     rc = run_pipelined(lane, prog, inputs, outputs, dims, whole, pieces);
@@ -1460,6 +1650,15 @@ void release_all() {
       p = nullptr;
     }
     lane->params_version = 0;
+    for (Stager* st : {&lane->stage_in, &lane->stage_out}) {
+      for (int k = 0; k < Stager::kSlots; ++k) {
+        if (st->slot[k] != nullptr) cudaFreeHost(st->slot[k]);
+        st->slot[k] = nullptr;
+        st->busy[k] = false;
+        st->out_bytes[k] = 0;
+      }
+      st->slot_bytes = 0;
+    }
   }
   g_params_host.clear();      // params must be set again before a launch
   g_params_version = 0;

@@ -233,3 +233,39 @@ def test_bad_elem_size_is_rejected():
   wrong = [np.zeros((64, 64), dtype=np.float64)]
   with pytest.raises(TypeError):
     library.run(wrong)
+
+
+@pytest.mark.parametrize('case', [
+    ('jacobi2d', 7, (1024, 300), {'depth': 4}),
+    ('denoise2d', 1, (777, 141), {}), ('heat3d', 3, (192, 48, 33), {'depth': 2}),
+    ('sobel2d', 1, (2048, 96), {})], ids=_ids)
+def test_pageable_and_pinned_host_buffers_give_the_same_bits(case, monkeypatch):
+  """Pageable caller memory (numpy arrays, the reference harness' `new`ed
+  arrays) goes through the runtime's pinned bounce buffers, a few host
+  threads copying; pinned memory is handed to the copy engine as it is.  Tiny
+  slots make every piece rotate through all of them, in and out."""
+  import torch
+  name, iterate, dims, options = case
+  orc = common.oracle(name, iterate)
+  inputs = common.random_inputs(orc, dims, seed=31)
+  want = orc.run(inputs)
+  library = _library(name, iterate, options)
+  monkeypatch.setenv('SODA_CUDA_STAGE_KB', '64')
+  for pieces, devices in (('1', None), ('3', None), ('2', '0,0')):
+    monkeypatch.setenv('SODA_CUDA_PIECES', pieces)
+    got = library.run(inputs, devices=devices)
+    for g, w in zip(got, want):
+      common.assert_bit_exact(g, w, '%s pageable, %s piece(s), devices %s' % (
+          name, pieces, devices), any_nan=name == 'denoise2d')
+  pinned_in = [torch.from_numpy(a).pin_memory() for a in inputs]
+  pinned_out = [torch.empty(w.shape, dtype=t.dtype).pin_memory()
+                for w, t in zip(want, [torch.from_numpy(w) for w in want])]
+  library.run([t.numpy() for t in pinned_in], [t.numpy() for t in pinned_out])
+  for g, w in zip(pinned_out, want):
+    common.assert_bit_exact(g.numpy(), w, '%s pinned' % name,
+                            any_nan=name == 'denoise2d')
+  monkeypatch.setenv('SODA_CUDA_STAGING', '0')      # the driver's own staging
+  got = library.run(inputs)
+  for g, w in zip(got, want):
+    common.assert_bit_exact(g, w, '%s unstaged' % name,
+                            any_nan=name == 'denoise2d')
