@@ -530,6 +530,24 @@ def main():
     # the result of the timed call against the device-resident run's: a
     # checksum over the valid region (not a parity test, a did-it-run test)
     e2e_value = cells * world * iterate / (e2e_ms * 1e6)
+    pageable = None
+    if not distributed:
+      # the same call on ordinary (pageable) numpy arrays, as a caller that
+      # does not pin its memory makes it: through the runtime's bounce buffers
+      page_in = np.array(np_in)          # a pageable copy
+      page_out = np.empty_like(page_in)
+      library.run([page_in], [page_out])
+      t0 = time.perf_counter()
+      for _ in range(2):
+        library.run([page_in], [page_out])
+      page_ms = (time.perf_counter() - t0) * 1e3 / 2
+      pageable = {'ms_per_step': page_ms,
+                  'value': cells * iterate / (page_ms * 1e6),
+                  'unit': 'GCell/s',
+                  'bit_identical_to_pinned': bool(
+                      np.array_equal(page_out.view(np.uint32),
+                                     np_out.view(np.uint32)))}
+      del page_in, page_out
     del host_in, host_out, np_in, np_out
     ceiling_ms = copy_ceiling(world, cells * 4)
     e2e = {'value': e2e_value, 'unit': 'GCell/s', 'ms_per_step': e2e_ms,
@@ -554,6 +572,7 @@ def main():
                        'back at once, cudaMemcpyAsync from pinned memory, no '
                        'compute: the host<->device capacity of this machine '
                        'at %d device(s)' % (world, cells * 4 / 1e9, world)},
+           'pageable_host_buffers': pageable,
            'numa_node_rank0': numa_node}
   barrier()
 
