@@ -78,16 +78,27 @@ def _candidates(program, limit):
     cap = 16 if program.dim == 2 else 4
     depths = [d for d in (1, 2, 4, 8, 16) if d <= min(program.iterate, cap)]
   grid = []
+  # programs with single-use locals: also with those spliced into their
+  # readers (fewer registers held across steps; it paid where the registers
+  # bought a taller tile: denoise3d, profiles/README.md capture r2o)
+  splices = (None, 1) if plan_mod.inline_single_use(program) else (None,)
   if program.dim == 2:
     for threads, groups, prefetch in itertools.product(
         (None, 64, 256), (None, 8), (None, 12, 36)):
       grid.append({'threads': threads, 'groups': groups, 'prefetch': prefetch})
+    grid += [{'inline': 1, 'threads': t} for t in (None, 64) if splices[-1]]
   else:
     vec = codegen.default_vec(program)
     rests = [None] + ([[32 * vec, r] for r in (32, 16, 8)]
                       if program.dim == 3 else [])
     for tile, prefetch in itertools.product(rests, (None, 1, 2, 3)):
       grid.append({'tile': tile, 'prefetch': prefetch})
+    if program.dim == 3:
+      # tall tiles with two vectors per thread
+      for inline, prefetch in itertools.product(splices, (1, 2)):
+        grid.append({'tile': [32 * vec, 32], 'threads': 512,
+                     'prefetch': prefetch, 'inline': inline})
+      grid += [{'inline': 1} for _ in splices[1:]]
   grid += [{'depth': depth} for depth in depths]
   chosen, seen = [], set()
   for options in grid:
