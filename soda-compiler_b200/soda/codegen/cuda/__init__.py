@@ -65,7 +65,7 @@ def add_arguments(parser):
       help='input planes requested ahead of the one being consumed')
   parser.add_argument(
       '--cuda-groups', type=int, dest='cuda_groups', metavar='N',
-      help='2-D kernels: TMA boxes in the per-warp input queue (4, 8, ..); '
+      help='2-D kernels: TMA boxes in the per-warp input queue (3, 4, 8, ..); '
       'a box holds prefetch / (N - 2) rows')
   parser.add_argument(
       '--cuda-min-blocks', type=int, dest='cuda_min_blocks', metavar='N',

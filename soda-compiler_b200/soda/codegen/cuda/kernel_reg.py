@@ -404,13 +404,13 @@ class _Emitter:
     this chunk) of every input into its slots."""
     p, lay = self.p, self.lay
     G, B = lay.groups, lay.box_rows
-    p.println('uint64_t* const bar = &bars[(%s) & %d];' % (box_code, G - 1))
+    p.println('uint64_t* const bar = &bars[(%s) %% %d];' % (box_code, G))
     p.println('soda::mbar_expect_tx(bar, %d);' % (
         B * sum(lay.row_bytes.values())))
     for node in lay.loaded_inputs:
-      p.println('soda::tma_load(queue + %d + ((%s) & %d) * %d, &a.in_map[%d], '
+      p.println('soda::tma_load(queue + %d + ((%s) %% %d) * %d, &a.in_map[%d], '
                 'bar, org0, base + (%s) * %d);' % (
-                    lay.queue_offset[node.index], box_code, G - 1,
+                    lay.queue_offset[node.index], box_code, G,
                     B * lay.row_bytes[node.index], node.input_index, box_code,
                     B))
 
@@ -475,13 +475,14 @@ class _Emitter:
     p.do_scope()
     self.flat_issue('box + %d' % (G - 2))
     p.un_scope()
-    p.println('soda::mbar_wait(&bars[box & %d], (box >> %d) & 1);' % (
-        G - 1, _log2(G)))
+    # (the queue holds G boxes, 3 or a power of two: constants, so the
+    # compiler turns these into masks and shifts where it can)
+    p.println('soda::mbar_wait(&bars[box %% %d], (box / %d) & 1);' % (G, G))
     p.un_scope()
     for node in lay.loaded_inputs:
-      p.println('const unsigned char* const rows_%s = queue + %d + (box & %d) * '
+      p.println('const unsigned char* const rows_%s = queue + %d + (box %% %d) * '
                 '%d + lane * %d;' % (
-                    node.ident, lay.queue_offset[node.index], G - 1,
+                    node.ident, lay.queue_offset[node.index], G,
                     B * lay.row_bytes[node.index], self.V * node.elem_size))
 
   def emit_flat_input(self, phase):

@@ -708,8 +708,8 @@ class RegSchedule(Schedule):
     # of its first use, into the slots of the box consumed before the previous
     # one.
     self.flat_groups = groups or FLAT_GROUPS
-    if self.flat_groups < 3 or self.flat_groups & (self.flat_groups - 1):
-      raise util.SemanticError('the input queue holds 4, 8, 16.. boxes')
+    if self.flat_groups < 3:
+      raise util.SemanticError('the input queue holds at least 3 boxes')
     self.paired = paired
     if paired:
       why = pairing_obstacle(program, depth)

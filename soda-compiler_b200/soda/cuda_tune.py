@@ -84,7 +84,7 @@ def _candidates(program, limit):
   splices = (None, 1) if plan_mod.inline_single_use(program) else (None,)
   if program.dim == 2:
     for threads, groups, prefetch in itertools.product(
-        (None, 64, 256), (None, 8), (None, 12, 36)):
+        (None, 64, 256), (None, 3, 8), (None, 12, 36)):
       grid.append({'threads': threads, 'groups': groups, 'prefetch': prefetch})
     grid += [{'inline': 1, 'threads': t} for t in (None, 64) if splices[-1]]
   else:

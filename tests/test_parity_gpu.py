@@ -56,6 +56,11 @@ CASES = [
     ('blur', 1, (2048, 128), {'style': 'ring'}),
     ('heat3d', 2, (192, 48, 33), {'style': 'ring'}),
     ('heat3d', 2, (256, 64, 40), {'tile': [128, 16], 'threads': 256}),
+    # a three-box input queue (one box in flight: less shared memory, more
+    # resident warps — the tuned choice of denoise2d)
+    ('jacobi2d', 8, (2048, 260), {'depth': 8, 'groups': 3}),
+    ('sobel2d', 1, (1101, 157), {'groups': 3}),
+    ('denoise2d', 1, (1024, 128), {'groups': 3, 'threads': 64}),
     # single-use locals spliced into their readers (--cuda-inline 1)
     ('denoise2d', 1, (777, 141), {'inline': 1}),
     ('denoise3d', 1, (93, 41, 37), {'inline': 1}),
