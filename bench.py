@@ -267,6 +267,10 @@ def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
         entry['host_level_applications'] = iterate
       runner = cuda_slab.SlabRunner(library, dims, rank, world,
                                     feedback=feedback)
+      # one GPU, the program's own iterate: the C ABI's device entry, as a
+      # caller with device arrays makes it (the slab runner adds ~15 us of
+      # Python per run, which is more than blur 2000 x 1000 takes)
+      direct = world == 1 and feedback is None
       owned = []
       generator = torch.Generator(device='cuda').manual_seed(1 + rank)
       for local_in in runner.inputs:
@@ -279,8 +283,15 @@ def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
                                      generator=generator).to(local_in.dtype))
       runner.load_local(owned)
       del owned
+      if direct:
+        outs = [torch.empty_like(t) for t in runner.buffers[0]]
+        stream = torch.cuda.current_stream().cuda_stream
+        run_once = lambda: library.run_device(runner.inputs, outs, dims,
+                                              iterate, stream)
+      else:
+        run_once = lambda: runner.run(iterate)
       for _ in range(2):
-        runner.run(iterate)
+        run_once()
       times = []
       cells = float(np.prod(dims))
       inner = 50 if cells < 1e7 else 1     # microsecond kernels: time a batch
@@ -289,7 +300,7 @@ def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
         start, stop = torch.cuda.Event(True), torch.cuda.Event(True)
         start.record()
         for _ in range(inner):
-          runner.run(iterate)
+          run_once()
         stop.record()
         torch.cuda.synchronize()
         times.append(max_over_ranks(start.elapsed_time(stop)) / inner)
@@ -301,6 +312,8 @@ def run_extra(rank, world, barrier, max_over_ranks, peak, reps=3):
           'temporal_depth': runner.plan(iterate)[0], 'passes': passes,
           'launches_rank0': runner.launches_per_run(iterate),
           'runs_per_timing': inner,
+          'entry': 'soda_cuda_run_device' if direct else
+                   'soda_cuda_launch per slab (soda/cuda_slab.py)',
           'roofline': {
               'bound': 'hbm', 'achieved': achieved, 'peak': peak * world,
               'unit': 'GB/s', 'frac': achieved / (peak * world),
