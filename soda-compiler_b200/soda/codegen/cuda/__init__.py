@@ -211,7 +211,14 @@ def _make_reg_schedule(program, depth, options, limit):
     warps = (options.threads or 128) // 32
     paired = (options.paired if options.paired is not None else
               plan_mod.pairing_obstacle(program, depth) is None)
-    groups = options.groups or plan_mod.FLAT_GROUPS
+    # boxes in the per-warp input queue: four (two in flight) for programs
+    # the HBM rate bounds; three for unpaired compute-bound ones, where the
+    # shared memory saved buys resident warps and one box in flight is ample
+    # (denoise2d 271 -> 318 GCell/s; sobel2d / blur / seidel2d lose 5-13 %
+    # with three, paired jacobi2d x8 is neutral: profiles capture r2v)
+    compute_bound = (not paired and plan_mod.arithmetic_weight(program) *
+                     depth >= 5 * plan_mod.bytes_per_cell(program))
+    groups = options.groups or (3 if compute_bound else plan_mod.FLAT_GROUPS)
     # rows per TMA box (measured, profiles/r1i): 6 keeps six blocks resident;
     # paired kernels hold fewer, fatter warps and want deeper queues
     prefetch = options.prefetch if options.prefetch is not None else (

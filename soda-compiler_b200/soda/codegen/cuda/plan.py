@@ -625,6 +625,33 @@ _PAIR_TOKEN = None
 FLAT_GROUPS = 4   # boxes in the input queue of a 2-D register kernel
 
 
+def arithmetic_weight(program):
+  """Rough count of instructions one cell of one iteration costs: operators of
+  the lowered expressions, a float division as 10, a math call as 15
+  (benchmarks, estimate / measured per cell: blur 8 / 20, sobel2d 16 / 23,
+  jacobi2d 5 / 5.7, denoise2d 68 / 85).  Only used to
+  tell compute-bound programs from bandwidth-bound ones."""
+  total = 0
+  for stage in program.stages:
+    lets, text = stage.render(lambda load: 'x',
+                              cast=lambda c_type, inner: '(%s)' % inner)
+    # an IEEE division is a dozen instructions, an integer division by a
+    # literal a multiply and a shift
+    division = 10 if util.is_float(stage.haoda_type) else 2
+    for piece in list(lets) + [text]:
+      total += sum(piece.count(op) for op in '+-*<>&|^?')
+      total += division * piece.count('/')
+    total += 15 * len(stage.calls())
+  return total
+
+
+def bytes_per_cell(program):
+  """Compulsory HBM traffic of one pass: every input read once, every output
+  written once."""
+  return sum(util.get_width_in_bytes(t)
+             for _, t in program.inputs + program.outputs)
+
+
 def pairing_obstacle(program, depth):
   """Why ``depth`` fused iterations of ``program`` cannot run two per
   instruction on packed f32x2 arithmetic (None if they can).
