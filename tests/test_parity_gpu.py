@@ -56,6 +56,10 @@ CASES = [
     ('blur', 1, (2048, 128), {'style': 'ring'}),
     ('heat3d', 2, (192, 48, 33), {'style': 'ring'}),
     ('heat3d', 2, (256, 64, 40), {'tile': [128, 16], 'threads': 256}),
+    # the tuned 3-D tile of the 1024^3 runs: 48 rows, 24 warps
+    ('heat3d', 4, (256, 100, 40), {'depth': 2, 'tile': [128, 48],
+                                   'threads': 768}),
+    ('jacobi3d', 2, (131, 97, 33), {'tile': [128, 48], 'threads': 768}),
     # a three-box input queue (one box in flight: less shared memory, more
     # resident warps — the tuned choice of denoise2d)
     ('jacobi2d', 8, (2048, 260), {'depth': 8, 'groups': 3}),
