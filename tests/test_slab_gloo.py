@@ -212,8 +212,11 @@ def test_face_decomposition_rules(monkeypatch):
   runner = runner_for('heat3d', (64, 64, 1024), 1, 4, 6)
   a = runner.begin - runner.local_begin
   assert runner._split(2, a, a + 256) == (a + 2, a + 256 - 2, 0)
-  # a slab of two blocks cannot give both away: minimal faces
+  # a slab of two blocks cannot give both away: quarter blocks instead, so
+  # that half the slab stays as interior to hide the exchange behind
   monkeypatch.delenv('SODA_CUDA_SLAB_FACES')
   runner = runner_for('heat3d', (64, 64, 256), 1, 4, 6)
   a = runner.begin - runner.local_begin
-  assert runner._split(2, a, a + 64) == (a + 2, a + 64 - 2, 0)
+  assert runner._split(2, a, a + 64) == (a + 16, a + 64 - 16, 16)
+  # too thin even for that (quarters shorter than the reach): minimal faces
+  assert runner._split(2, a, a + 6) == (a + 2, a + 6 - 2, 0)
