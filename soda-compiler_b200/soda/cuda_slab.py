@@ -326,13 +326,15 @@ class SlabRunner:
       chunk = self._chunk_cache[key] if mode == 'chunk' else 0
     if chunk:
       round_up = lambda n: -(-n // chunk) * chunk
-      if round_up(need_lo) + round_up(need_hi) >= b - a:
-        # thin slab, coarse blocks (1024^3 on 8 GPUs: 128 planes in 2 blocks
-        # of 64): whole-block faces would leave no interior to hide the
-        # exchange behind.  Quarter blocks instead — faces of one block each,
-        # half the slab as interior (heat3d, 128 planes per rank: 4.67 ->
-        # 4.50 ms per 32 iterations, capture r3a).
-        chunk = -(-(b - a) // 4)
+      # Thin slab, coarse blocks (1024^3 on 8 GPUs: 128 planes in 2 blocks of
+      # 64): whole-block faces would leave little or no interior to hide the
+      # exchange behind, and the ranks at the ends of the grid, with one face,
+      # would run two 64-plane blocks back to back.  No block longer than a
+      # quarter of the slab: faces of one block each, at least half the slab
+      # as interior (heat3d, 128 planes per rank: 4.69 -> 4.51 ms per 32
+      # iterations, jacobi3d 4.19 -> 4.01; 3, 5, 6 or 8 blocks are slower:
+      # captures r3a-r3d).
+      chunk = min(chunk, -(-(b - a) // 4))
       if (chunk >= max(need_lo, need_hi, self.library.lead_rows(depth), 1) and
           round_up(need_lo) + round_up(need_hi) < b - a):
         need_lo, need_hi = round_up(need_lo), round_up(need_hi)
