@@ -251,7 +251,12 @@ def _make_reg_schedule(program, depth, options, limit):
                                'cells wide' % (32 * vec))
     rests = [tuple(options.tile[1:])]
   elif program.dim == 3:
+    # fused iterations widen the halo: 48-row tiles keep more of each tile
+    # (capture r3h: heat3d x4 1072 -> 1109 GCell/s, 768^3 x3 881 -> 934);
+    # single sweeps are HBM-bound and lose 1 % to the fewer, larger blocks
     rests = [(32,), (16,), (8,)]
+    if depth > 1 and plan_mod.max_elem_size(program) <= 4:
+      rests.insert(0, (48,))
   else:
     rests = [(8, 4), (4, 4)]
   prefetches = ([options.prefetch] if options.prefetch is not None
@@ -262,7 +267,9 @@ def _make_reg_schedule(program, depth, options, limit):
     for prefetch in prefetches:
       # two vectors per thread halve the shuffles and barriers per cell, but
       # only while the register histories leave room for the working set
+      tall = rows > 32 and not options.tile
       warp_choices = ([options.threads // 32] if options.threads else
+                      [rows // 2] if tall else
                       [max(1, min(16, rows // 2)), max(1, min(16, rows))])
       try:
         for warps in warp_choices:
@@ -274,6 +281,9 @@ def _make_reg_schedule(program, depth, options, limit):
         total = kernel_reg_mod.Layout(sched).total
       except util.SemanticError as e:
         problem = problem or e
+        continue
+      # 24 warps leave 85 registers a thread: light histories only
+      if tall and history_registers(sched) > REG_HISTORY_3D // 2:
         continue
       # one block of 512 threads per SM is the design point whenever the
       # histories are light: then the whole shared memory is the block's

@@ -374,6 +374,13 @@ class _Emitter:
       p.println('#pragma unroll')
       p.println('for (int j = 0; j < %d; ++j) fast_n%d[j] = fast%d[j] ? ok_n%d '
                 ': 0u;' % (self.VPT, n, n, n))
+      if self.V == 2:
+        # likewise the steps it stores cell by cell (see emit_stage)
+        p.println('unsigned slow_n%d[%d];' % (n, self.VPT))
+        p.println('#pragma unroll')
+        p.println('for (int j = 0; j < %d; ++j) slow_n%d[j] = own[j] ? '
+                  'static_cast<unsigned>(mine_hi%d - mine_lo%d) : 0u;' % (
+                      self.VPT, n, n, n))
       p.println('%s* op%d[%d];   // row of step 0 (dereferenced only inside '
                 'the window)' % (node.c_type, n, self.VPT))
       p.println('#pragma unroll')
@@ -682,8 +689,9 @@ class _Emitter:
       n = node.output_index
       p.println('const bool row_ok = static_cast<unsigned>(ii - ok_lo%d) < '
                 'ok_n%d;' % (n, n))
-      p.println('const bool row_mine = ii >= mine_lo%d && ii < mine_hi%d;' % (
-          n, n))
+      if V != 2:
+        p.println('const bool row_mine = ii >= mine_lo%d && ii < mine_hi%d;'
+                  % (n, n))
     p.println('#pragma unroll')
     p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
     p.do_scope()
@@ -799,7 +807,13 @@ class _Emitter:
       p.println('soda::st_pack_global<%s, %d>(op%d[j], o);' % (
           node.c_type, V, n))
       p.un_scope()
-      p.println('else if (row_mine && own[j])')
+      # two-cell vectors: ptxas 12.9 keeps the two `own` bits in predicates and
+      # was seen to fold `row_mine && own[j]` into the wrong 3-input LUT
+      # (fully owned vectors skipped in two steps of a trip: dbl3d, 64x48
+      # tile, -O3 only) -- one unsigned compare against a
+      # per-thread count, like the fast test, leaves it nothing to fold
+      p.println('else if (static_cast<unsigned>(ii - mine_lo%d) < slow_n%d[j])'
+                % (n, n) if V == 2 else 'else if (row_mine && own[j])')
       p.do_scope()
       p.println('// tile or grid edge: cells outside the valid region are '
                 'stored as 0')

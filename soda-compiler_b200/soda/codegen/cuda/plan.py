@@ -652,6 +652,11 @@ def bytes_per_cell(program):
              for _, t in program.inputs + program.outputs)
 
 
+def max_elem_size(program):
+  """Bytes of the widest tensor cell of the program."""
+  return max(util.get_width_in_bytes(t) for t in program.types.values())
+
+
 def pairing_obstacle(program, depth):
   """Why ``depth`` fused iterations of ``program`` cannot run two per
   instruction on packed f32x2 arithmetic (None if they can).

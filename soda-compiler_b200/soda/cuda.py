@@ -20,6 +20,7 @@ import io
 import os
 import shutil
 import subprocess
+import threading
 
 import numpy as np
 
@@ -141,7 +142,8 @@ def build(stencil, build_dir=None, options=None, fast_math=False,
     handle.write(kernel_src)
   with open(host_path, 'w') as handle:
     handle.write(host_src)
-  tmp = '%s.%d.tmp' % (lib, os.getpid())   # concurrent builders do not collide
+  # concurrent builders (processes or threads) do not collide
+  tmp = '%s.%d.%d.tmp' % (lib, os.getpid(), threading.get_ident())
   command = nvcc_command([kernel_path, host_path, runtime], tmp,
                          fast_math, ['-Xptxas', '-v'] if verbose else [])
   done = subprocess.run(command, stdout=subprocess.PIPE,

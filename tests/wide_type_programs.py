@@ -19,6 +19,9 @@ output int64: o(0, 0) = s(0, 0) - s(-1, 0) * 5 + (s(0, -1) % 11)
 local uint32: s(0, 0, 0) = a(0, 0, 0) * 2654435761 + a(0, 1, 0) - a(0, 0, 1)
 output uint32: o(0, 0, 0) = s(0, 0, 0) + s(1, 0, 0) * s(0, -1, 0) - s(0, 0, -1) / 5
 '''),
+    'i64vol': (2, '''input int64: a(16, 8, *)
+output int64: o(0, 0, 0) = a(0, 0, 0) * 3 + a(1, 0, 0) - a(0, -1, 0) + a(0, 0, 1)
+'''),
     'mixed': (1, '''input float: a(32, *)
 local double: d(0, 0) = a(0, 0) * 0.1 + a(1, 0)
 output float: o(0, 0) = d(0, 0) + d(0, -1) * a(-1, 0)
@@ -33,6 +36,15 @@ CASES = [
     ('u32vol', (256, 48, 40), {}), ('u32vol', (131, 35, 29), {}),
     ('mixed', (2048, 96), {}), ('mixed', (777, 131), {}),
     ('dbl2d', (2048, 160), {'style': 'ring'}),
+    ('dbl2d', (1061, 97), {'style': 'ring'}),
+    ('dbl3d', (131, 35, 29), {'style': 'ring'}),
+    # 48-row tiles in 24 warps on two-cell vectors, rows not 16-byte aligned
+    # (cell-by-cell stores): the configuration ptxas 12.9 miscompiled before
+    # the emitter's slow-path test became one compare
+    ('dbl3d', (131, 35, 29), {'tile': [64, 48], 'threads': 768}),
+    ('dbl3d', (130, 50, 29), {'tile': [64, 48], 'threads': 768}),
+    ('i64vol', (131, 35, 29), {}),
+    ('i64vol', (131, 35, 29), {'tile': [64, 48], 'threads': 768}),
 ]
 
 
