@@ -192,12 +192,37 @@ __device__ __forceinline__ void move_dense(T* g, int n, T* buf, int phase,
   }
 }
 
+// Shared-memory bank rotation for the strided side.  Lane l holds word l of a
+// run; its cell k lives (word bytes) * kBanks bytes after lane l - 1's cell k,
+// so with every lane on the same k lanes a few apart share a bank
+// (two banks of 16-bit cells: a 4-way conflict on every access, ~260 of the
+// ~290 wavefronts a 4 KB row cost).  Round r therefore moves cell
+// (r + group) mod N of each lane, group = the lane's index among the lanes it
+// would collide with: every lane still moves each of its N cells once, and
+// the lanes of one access spread over the banks.
+template <int kWordBytes, int kStride>
+__device__ __forceinline__ int conflict_group(int lane) {
+  constexpr int kSpan = kWordBytes * kStride / 4;     // lane stride in banks
+  constexpr int kPeriod = kSpan % 32 == 0  ? 1
+                          : kSpan % 16 == 0 ? 2
+                          : kSpan % 8 == 0  ? 4
+                          : kSpan % 4 == 0  ? 8
+                          : kSpan % 2 == 0  ? 16
+                                            : 32;
+  return lane / kPeriod;
+}
+
+template <typename T>
+__device__ __forceinline__ T cell_of(uint64_t word, int k) {
+  return static_cast<T>(word >> (k * 8 * static_cast<int>(sizeof(T))));
+}
+
 // Bank run g[0..count) <-> shared elements sm[e * stride], one 4- or 8-byte
 // word of the run per lane and access (the head and tail that do not fill an aligned word
 // move element-wise).
-template <typename T, bool kToShared>
-__device__ __forceinline__ void move_strided(T* g, int count, T* sm, int stride,
-                                             int lane) {
+template <typename T, bool kToShared, int kStride>
+__device__ __forceinline__ void move_strided(T* g, int count, T* sm, int lane) {
+  constexpr int stride = kStride;
   // measured (capture r2j, blur 32768^2 u16, two banks): loads want 8-byte
   // words (unpack 4015 -> 4290 GB/s), stores 4-byte ones (pack 5642 vs 4938)
   constexpr int kWordBytes = (kToShared || sizeof(T) == 8) ? 8 : 4;
@@ -224,6 +249,9 @@ __device__ __forceinline__ void move_strided(T* g, int count, T* sm, int stride,
   }
   Word* const body = reinterpret_cast<Word*>(g + head);
   T* const sm_body = sm + head * stride;
+  // (pack reads the buffer in 4-byte words, a 2-way conflict at most, and
+  // measured 2 % slower rotated: 5572 -> 5432 GB/s)
+  const int group = kToShared ? conflict_group<kWordBytes, kStride>(lane) : 0;
   // loads: twice as many in flight as on the 16-byte side
   constexpr int kUnroll = kToShared ? 2 * kWireUnroll : kWireUnroll;
   for (int w0 = lane; w0 < words; w0 += 32 * kUnroll) {
@@ -239,13 +267,19 @@ __device__ __forceinline__ void move_strided(T* g, int count, T* sm, int stride,
       if (w >= words) break;
       if (kToShared) {
 #pragma unroll
-        for (int k = 0; k < N; ++k)
-          sm_body[(w * N + k) * stride] = cells[u].cell[k];
+        for (int r = 0; r < N; ++r) {
+          const int k = (r + group) & (N - 1);
+          sm_body[(w * N + k) * stride] = cell_of<T>(cells[u].word, k);
+        }
       } else {
+        uint64_t word = 0;
 #pragma unroll
-        for (int k = 0; k < N; ++k)
-          cells[u].cell[k] = sm_body[(w * N + k) * stride];
-        body[w] = cells[u].word;
+        for (int r = 0; r < N; ++r) {
+          const int k = (r + group) & (N - 1);
+          word |= static_cast<uint64_t>(sm_body[(w * N + k) * stride])
+                  << (k * 8 * static_cast<int>(sizeof(T)));
+        }
+        body[w] = static_cast<Word>(word);
       }
     }
   }
@@ -283,11 +317,165 @@ wire_kernel_staged(const __grid_constant__ soda_fpga_layout_t a, T* dense,
       const int count = (n - skip + kBanks - 1) / kBanks;
       T* const run = static_cast<T*>(banks.ptr[a.bank_vec[b]]) +
                      (first_o + skip) / kBanks;
-      move_strided<T, !kPack>(run, count, buf + phase + skip, kBanks, lane);
+      move_strided<T, !kPack, kBanks>(run, count, buf + phase + skip, lane);
     }
     __syncwarp();
     if (!kPack) move_dense<T, false>(row_dense, n, buf, phase, lane);
     __syncwarp();       // the buffer is reused by this warp's next row
+  }
+}
+
+// ---- unpack, software-pipelined ------------------------------------------------
+//
+// In the staged kernel a warp alternates between its two sides: while it
+// writes a row's dense run it has no bank loads in flight, and unpack — whose
+// scattered side is the load side, 8 bytes per lane and access — ran at 68 %
+// of the HBM rate where pack reaches 86 %.  Here a warp fetches the bank runs
+// of its NEXT row into registers before it writes the current row's dense
+// run: a whole row per warp stays in flight at all times.  The prefetched
+// words stay in registers, so the warp still needs one row buffer.  Rows
+// whose bank runs exceed the register budget (kWireFetchWords 8-byte words
+// per lane over all banks: 4 KB of row) take the staged kernel.
+// Measured (blur 32768^2 u16, tile 2000, two banks; capture r3j): staged
+// 4464 GB/s; pipelined 4644; with the bank rotation below staged 4908,
+// pipelined 5205 (79 % of the HBM rate).  Two blocks of 8 warps per SM: the
+// prefetched row costs ~118 registers, and three blocks spill (3468).
+constexpr int kWireFetchWords = 16;
+
+template <typename T>
+struct BankRun {
+  const T* run;   // first cell of the row in this bank
+  int count;      // cells of the row in this bank
+  int skip;       // the row's first cell that lands in this bank
+};
+
+template <typename T, int kBanks>
+__device__ __forceinline__ BankRun<T> bank_run(const soda_fpga_layout_t& a,
+                                               const Banks& banks, const Row& r,
+                                               int b) {
+  const long long first_o = r.stream + r.i_lo;
+  const int n = r.i_hi - r.i_lo;
+  BankRun<T> g;
+  g.skip = static_cast<int>(((b - first_o) % kBanks + kBanks) % kBanks);
+  g.count = g.skip >= n ? 0 : (n - g.skip + kBanks - 1) / kBanks;
+  g.run = static_cast<const T*>(banks.ptr[a.bank_vec[b]]) +
+          (first_o + g.skip) / kBanks;
+  return g;
+}
+
+// What a lane holds of one bank run: aligned 8-byte words `lane + 32 u` of
+// the body, and one cell of the unaligned head and tail each.
+template <typename T, int kWords>
+struct Fetched {
+  uint64_t body[kWords];
+  T head, tail;
+};
+
+template <typename T>
+struct RunSplit {
+  int head, words, tail;
+};
+
+template <typename T>
+__device__ __forceinline__ RunSplit<T> split_run(const T* g, int count) {
+  constexpr int N = 8 / static_cast<int>(sizeof(T));
+  const int misaligned =
+      static_cast<int>((reinterpret_cast<uintptr_t>(g) & 7) / sizeof(T));
+  RunSplit<T> s;
+  s.head = min(count, (N - misaligned) % N);
+  s.words = (count - s.head) / N;
+  s.tail = count - s.head - s.words * N;
+  return s;
+}
+
+template <typename T, int kWords>
+__device__ __forceinline__ void fetch_run(const BankRun<T>& g, int lane,
+                                          Fetched<T, kWords>* f) {
+  constexpr int N = 8 / static_cast<int>(sizeof(T));
+  const RunSplit<T> s = split_run(g.run, g.count);
+  if (lane < s.head) f->head = g.run[lane];
+  if (lane < s.tail) f->tail = g.run[s.head + s.words * N + lane];
+  const uint64_t* const body =
+      reinterpret_cast<const uint64_t*>(g.run + s.head);
+#pragma unroll
+  for (int u = 0; u < kWords; ++u)
+    if (lane + 32 * u < s.words) f->body[u] = body[lane + 32 * u];
+}
+
+// The fetched cells into the row buffer: cell e of the run at sm[e * stride].
+template <typename T, int kWords, int kStride>
+__device__ __forceinline__ void place_run(const BankRun<T>& g, int lane,
+                                          const Fetched<T, kWords>& f, T* sm) {
+  constexpr int N = 8 / static_cast<int>(sizeof(T));
+  constexpr int stride = kStride;
+  const int group = conflict_group<8, kStride>(lane);
+  const RunSplit<T> s = split_run(g.run, g.count);
+  if (lane < s.head) sm[lane * stride] = f.head;
+  if (lane < s.tail) sm[(s.head + s.words * N + lane) * stride] = f.tail;
+  T* const sm_body = sm + s.head * stride;
+#pragma unroll
+  for (int u = 0; u < kWords; ++u) {
+    const int w = lane + 32 * u;
+    if (w < s.words) {
+#pragma unroll
+      for (int r = 0; r < N; ++r) {
+        const int k = (r + group) & (N - 1);
+        sm_body[(w * N + k) * stride] = cell_of<T>(f.body[u], k);
+      }
+    }
+  }
+}
+
+template <typename T, int kBanks>
+__global__ void __launch_bounds__(32 * kWireWarps, 2)
+wire_unpack_pipelined(const __grid_constant__ soda_fpga_layout_t a, T* dense,
+                      const __grid_constant__ Banks banks, long long rows) {
+  extern __shared__ __align__(16) unsigned char staged_raw[];
+  constexpr int W = 16 / sizeof(T);
+  constexpr int kWords = kWireFetchWords / kBanks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pitch = (a.tile_size[0] + 2 * W + W - 1) / W * W;
+  T* const buf = reinterpret_cast<T*>(staged_raw) + warp * pitch;
+  const long long step = static_cast<long long>(gridDim.x) * kWireWarps;
+  long long row = static_cast<long long>(blockIdx.x) * kWireWarps + warp;
+  Row next;
+  // the warp's next row with anything to move (uniform over the warp)
+  auto advance = [&]() {
+    for (; row < rows; row += step) {
+      next = decode_row<false>(a, row, blockIdx.y);
+      if (next.inside && next.i_hi > next.i_lo) return true;
+    }
+    return false;
+  };
+  if (!advance()) return;
+  Fetched<T, kWords> fetched[kBanks];
+#pragma unroll
+  for (int b = 0; b < kBanks; ++b)
+    fetch_run<T, kWords>(bank_run<T, kBanks>(a, banks, next, b), lane,
+                         &fetched[b]);
+  for (;;) {
+    const Row r = next;
+    const int n = r.i_hi - r.i_lo;
+    T* const row_dense = dense + r.original + r.i_lo;
+    const int phase = static_cast<int>(
+        (reinterpret_cast<uintptr_t>(row_dense) & 15) / sizeof(T));
+#pragma unroll
+    for (int b = 0; b < kBanks; ++b) {
+      const BankRun<T> g = bank_run<T, kBanks>(a, banks, r, b);
+      place_run<T, kWords, kBanks>(g, lane, fetched[b], buf + phase + g.skip);
+    }
+    __syncwarp();
+    row += step;
+    const bool more = advance();
+    if (more) {
+#pragma unroll
+      for (int b = 0; b < kBanks; ++b)
+        fetch_run<T, kWords>(bank_run<T, kBanks>(a, banks, next, b), lane,
+                             &fetched[b]);
+    }
+    move_dense<T, false>(row_dense, n, buf, phase, lane);
+    __syncwarp();       // the buffer takes the next row
+    if (!more) break;
   }
 }
 
@@ -305,12 +493,26 @@ int launch(const soda_fpga_layout_t& a, T* dense, const Banks& table,
   bool staged = a.tile_size[0] * sizeof(T) >= 512;
   if (env != nullptr && (env[0] == '0' || env[0] == '1')) staged = env[0] == '1';
   staged = staged && smem <= 200 * 1024;
+  // unpack: the pipelined kernel where a row's bank runs fit its registers
+  // (SODA_FPGA_PIPELINED=0: the staged kernel)
+  const char* piped = getenv("SODA_FPGA_PIPELINED");
+  const bool pipelined =
+      !kPack && !(piped != nullptr && piped[0] == '0') &&
+      (static_cast<size_t>(a.tile_size[0]) / a.num_bank + 2) * sizeof(T) <=
+          static_cast<size_t>(kWireFetchWords / a.num_bank) * 256;
   const long long rows = grid.x;
   // enough blocks for every SM to hold its fill, each warp walking ~4 rows
   const long long wanted = (rows + kWireWarps * 4 - 1) / (kWireWarps * 4);
   dim3 sgrid(static_cast<unsigned>(std::max<long long>(1, wanted)), grid.y);
 #define SODA_WIRE_LAUNCH(kBanks)                                              \
-  if (staged) {                                                               \
+  if (staged && pipelined) {                                                  \
+    auto fn = wire_unpack_pipelined<T, kBanks>;                               \
+    if (smem > 48 * 1024 &&                                                   \
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             static_cast<int>(smem)) != cudaSuccess)          \
+      return kLaunchFailed;                                                   \
+    fn<<<sgrid, 32 * kWireWarps, smem, s>>>(a, dense, table, rows);           \
+  } else if (staged) {                                                        \
     auto fn = wire_kernel_staged<T, kPack, kBanks>;                           \
     if (smem > 48 * 1024 &&                                                   \
         cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, \

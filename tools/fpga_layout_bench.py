@@ -36,8 +36,11 @@ def main():
       ('pack staged', lambda: fpga_layout.pack(layout, name_in, dense,
                                                banks_in)),
       ('unpack staged', lambda: fpga_layout.unpack(layout, name_out, out,
-                                                   banks_out))):
-    os.environ['SODA_FPGA_STAGED'] = '1' if 'staged' in what else '0'
+                                                   banks_out)),
+      ('unpack piped', lambda: fpga_layout.unpack(layout, name_out, out,
+                                                  banks_out))):
+    os.environ['SODA_FPGA_STAGED'] = '0' if what in ('pack', 'unpack') else '1'
+    os.environ['SODA_FPGA_PIPELINED'] = '1' if 'piped' in what else '0'
     for _ in range(3):
       call()
     torch.cuda.synchronize()
