@@ -365,7 +365,7 @@ def history_registers(sched):
   return total
 
 
-def make_schedules(program, options=None):
+def make_schedules(program, options=None, fast_math=False):
   """The kernel variants to compile: the main temporal depth and, when it does
   not divide ``iterate``, the depth of the remainder.
 
@@ -379,7 +379,8 @@ def make_schedules(program, options=None):
   options = options or Options()
   check_supported(program)
   if options.is_default():
-    found = tuned_mod.lookup(program)     # soda.cuda_tune's winner, if any
+    # soda.cuda_tune's winner, if any (``fast_math``: the one of that build)
+    found = tuned_mod.lookup(program, fast_math=fast_math)
     if found:
       options = Options(**found)
   spliced = plan_mod.inline_single_use(program) if options.inline else None
@@ -495,8 +496,8 @@ def print_code(stencil, args):
     if results and results[0][1]:
       cuda_tune.record(program, dims, results[0][0], results[0][1])
   if kernel_file is not None:
-    schedules = make_schedules(program, Options.from_args(args))
     fast = bool(getattr(args, 'cuda_fast', False))
+    schedules = make_schedules(program, Options.from_args(args), fast)
     _emit(kernel_file, lambda f: print_kernel(program, schedules, f, fast))
   if host_file is not None:
     _emit(host_file, lambda f: host_mod.print_code(program, f))

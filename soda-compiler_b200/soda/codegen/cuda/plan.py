@@ -125,8 +125,14 @@ class Stage:
       node.visit(note)
     return names
 
+  def top_division(self):
+    """True if the statement is a quotient at its top: `A / B` or
+    `A * .. / B` (the chain's last operator is the division) and has no lets."""
+    ops = getattr(self.expr, 'operator', ())
+    return bool(ops) and ops[-1] == '/' and not self.lets
+
   def render(self, ref_code, call_prefix='', let_prefix='', shift=None,
-             cast=None):
+             cast=None, split_top=False):
     """``(let lines, expression)`` as C, each Ref replaced by ``ref_code(load)``.
 
     The expression text is the IR's own ``c_expr`` lowering of the tree with
@@ -136,6 +142,9 @@ class Stage:
     inlined statement becomes ``cast(its C type, its expression)`` — by
     default ``soda::store_cast<T>(..)``, the rounding its array would apply.
     ``call_prefix`` / ``let_prefix`` rename math calls and let variables.
+    ``split_top`` (statements with ``top_division``): the expression comes
+    back as ``(numerator, denominator)``; a chain `a * b / c` folds from the
+    left as C does, so its numerator is `(a * b)`.
     """
     if cast is None:
       cast = lambda c_type, text: 'soda::store_cast<%s>(%s)' % (c_type, text)
@@ -163,6 +172,13 @@ class Stage:
     lets = ['const %s %s%s = %s;' % (let.c_type, let_prefix, let.name,
                                      let.expr.visit(swap).c_expr)
             for let in self.lets]
+    if split_top:
+      assert self.top_division()
+      texts = [node.visit(swap).c_expr for node in self.expr.operand]
+      numerator = texts[0]
+      for op, rhs in zip(self.expr.operator[:-1], texts[1:-1]):
+        numerator = '(%s %s %s)' % (numerator, op, rhs)
+      return lets, (numerator, texts[-1])
     return lets, self.expr.visit(swap).c_expr
 
 

@@ -46,12 +46,19 @@ def load_table(path=None):
   return _cache[path][1]
 
 
-def lookup(program, path=None):
-  """The tuned ``Options`` keywords of ``program``, or None."""
+def lookup(program, path=None, fast_math=False):
+  """The tuned ``Options`` keywords of ``program``, or None.  An entry may
+  hold ``options_fast`` for the fast-math build, whose kernels have other
+  register needs than the exact ones (denoise3d: one vector per thread in 28
+  warps exact, two vectors in 16 warps fast)."""
   if os.environ.get('SODA_CUDA_TUNED', '1') == '0':
     return None
   entry = load_table(path).get(signature(program))
-  return dict(entry['options']) if entry else None
+  if not entry:
+    return None
+  if fast_math and 'options_fast' in entry:
+    return dict(entry['options_fast'])
+  return dict(entry['options'])
 
 
 def record(program, dims, ms, options, device='', path=None):

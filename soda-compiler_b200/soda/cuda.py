@@ -87,7 +87,7 @@ class Stats(ctypes.Structure):
 def generate_sources(stencil, options=None, fast_math=False):
   """``(program, kernel source, host source)`` for a Stencil."""
   program = plan_mod.extract_program(stencil)
-  schedules = codegen.make_schedules(program, options)
+  schedules = codegen.make_schedules(program, options, fast_math)
   kernel, host = io.StringIO(), io.StringIO()
   codegen.print_kernel(program, schedules, kernel, fast_math)
   host_gen.print_code(program, host)

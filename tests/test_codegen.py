@@ -207,3 +207,47 @@ def test_let_right_hand_sides_keep_their_parentheses(tmp_path, monkeypatch):
             str(tmp_path / 'k.o')],
         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert done.returncode == 0, ep.program(seed) + done.stdout[-1500:]
+
+
+def test_top_level_quotients_are_batched_per_vector():
+  """A float statement that is a quotient at its top is emitted as pairs,
+  soda::div_try on each pair, and the plain quotients under one `if (rare)`
+  per vector (kernel_reg.batches_rare_paths); the numerator of a chain
+  `a * b / c` is `(a * b)`."""
+  import io
+  program = plan.extract_program(common.stencil('denoise3d'))
+  stages = {stage.name: stage for stage in program.stages}
+  assert stages['g'].top_division() and stages['r1'].top_division()
+  assert stages['output'].top_division()
+  assert not stages['r0'].top_division()      # u * f * (1.0f / 0.03f)
+  assert not stages['diff_u'].top_division()
+  _, (num, den) = stages['g'].render(lambda load: 'x', call_prefix='soda_fn_',
+                                     split_top=True)
+  assert num == '1.0f' and den.startswith('soda_fn_sqrt(')
+  chain = core.Stencil.from_text(
+      'kernel: q\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+      'input float: a(32, *)\n'
+      'output float: o(0, 0) = a(0, 0) * a(1, 0) / a(0, 1)\n')
+  stage = plan.extract_program(chain).stages[0]
+  assert stage.top_division()
+  _, (num, den) = stage.render(lambda load: 'a%d%d' % tuple(load.off),
+                               split_top=True)
+  assert (num, den) == ('(a00 * a10)', 'a01')
+  out = io.StringIO()
+  codegen.print_kernel(program, codegen.make_schedules(program), out)
+  text = out.getvalue()
+  # the shipped denoise3d schedule splices r1 into the output statement (a
+  # spliced quotient keeps the compiler's division): two batched per step
+  steps = text.count('// g: plane')
+  assert steps > 0
+  assert text.count('soda::div_try(num0, den0, rare)') == 2 * steps
+  assert 'if (rare)' in text
+  # integer and double statements keep the plain form
+  ints = core.Stencil.from_text(
+      'kernel: q\nburst width: 64\nunroll factor: 1\niterate: 1\n'
+      'input int32: a(32, *)\n'
+      'output int32: o(0, 0) = (a(0, 0) + a(1, 0)) / 3\n')
+  program = plan.extract_program(ints)
+  out = io.StringIO()
+  codegen.print_kernel(program, codegen.make_schedules(program), out)
+  assert 'div_try' not in out.getvalue()

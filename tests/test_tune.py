@@ -92,3 +92,29 @@ def test_tune_picks_the_fastest_and_discards_wrong_results(monkeypatch):
   assert results == [(2.0, {'threads': 64}), (3.0, {})]
   assert any('DISCARDED' in line for line in lines)
   assert any('build failed' in line for line in lines)
+
+
+def test_an_entry_may_tune_the_fast_build_separately(tmp_path, monkeypatch):
+  """``options_fast``: the fast-math kernels of a program have other register
+  needs than the exact ones (shipped: denoise3d)."""
+  table = tmp_path / 'tuned.json'
+  monkeypatch.setattr(tuned, 'TABLE_PATH', str(table))
+  monkeypatch.delenv('SODA_CUDA_TUNED', raising=False)
+  program = plan.extract_program(common.stencil('jacobi2d', 64))
+  cuda_tune.record(program, (4096, 4096), 1.25, {'depth': 4}, 'test device')
+  data = json.loads(table.read_text())
+  data[tuned.signature(program)]['options_fast'] = {'depth': 2}
+  table.write_text(json.dumps(data))
+  assert codegen.make_schedules(program)[0].depth == 4
+  assert codegen.make_schedules(program, fast_math=True)[0].depth == 2
+  assert tuned.lookup(program) == {'depth': 4}
+  assert tuned.lookup(program, fast_math=True) == {'depth': 2}
+
+
+def test_shipped_denoise3d_entry_distinguishes_the_builds(monkeypatch):
+  monkeypatch.delenv('SODA_CUDA_TUNED', raising=False)
+  program = plan.extract_program(common.stencil('denoise3d'))
+  exact = codegen.make_schedules(program)[0]
+  fast = codegen.make_schedules(program, fast_math=True)[0]
+  assert (tuple(exact.tile), exact.threads) == ((128, 28), 896)
+  assert (tuple(fast.tile), fast.threads) == ((128, 32), 512)
