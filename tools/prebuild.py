@@ -96,6 +96,10 @@ def main():
     import wide_type_programs
     for name, _, options in wide_type_programs.CASES:
       jobs.append((name, wide_type_programs.stencil_of(name), options))
+    import test_quotients_gpu
+    for name, (body, _) in test_quotients_gpu.PROGRAMS.items():
+      stencil = core.Stencil.from_text(test_quotients_gpu.HEADER % name + body)
+      jobs += [(name, stencil, {}), (name, stencil, {'style': 'ring'})]
     import test_fastmath_gpu
     for name, iterate, _ in test_fastmath_gpu.CASES:
       jobs.append((name, iterate, {'fast': 1}))
