@@ -704,13 +704,31 @@ class _Emitter:
         fresh.append((parent, age, c, var))
         p.println('%s %s[%d];' % (self.ctype(parent), var, self.VPT))
     p.do_scope()
+    # A block runs its lead-in steps and the surplus steps that fill its last
+    # trip with every stage; the rows the LAST stage would produce there are
+    # not this block's to store, and when nothing reads that stage (a final
+    # output, no history, no shared plane) the whole stage is skipped for the
+    # step — a branch the block takes as one.  3-D kernels only: their blocks
+    # are tens of rows long (4-8 such steps in 30-70), the 2-D strips
+    # thousands.
+    skips = (node.output_index is not None and not sched.paired and
+             not self.flat and node is sched.stage_nodes[-1] and
+             node.hist_oldest is None and node.index not in lay.ring_offset)
     if node.output_index is not None:
       n = node.output_index
       p.println('const bool row_ok = static_cast<unsigned>(ii - ok_lo%d) < '
                 'ok_n%d;' % (n, n))
-      if V != 2:
+      if V != 2 or skips:
         p.println('const bool row_mine = ii >= mine_lo%d && ii < mine_hi%d;'
                   % (n, n))
+    if skips:
+      p.println('if (!row_mine)')
+      p.do_scope()
+      p.println('#pragma unroll')
+      p.println('for (int j = 0; j < %d; ++j) op%d[j] += a.stride[%d];' % (
+          self.VPT, node.output_index, s))
+      p.un_scope()
+      p.println('else')
     p.println('#pragma unroll')
     p.println('for (int j = 0; j < %d; ++j)' % self.VPT)
     p.do_scope()
