@@ -1,6 +1,14 @@
+"""A/B timing of two builds of the same programs on one box (developer tool):
+
+  build the libraries of two source states into  tools/ab/old  and
+  tools/ab/new  (soda.cuda.build(stencil, build_dir=...)), then run this file
+  on a GPU.  Used for captures r3s / r3t (profiles/README.md): box-to-box
+  spread is +-3 %, so small kernel changes are compared on the same box,
+  alternating, twice each.
+"""
 import os, sys, glob
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for sub in ('soda-compiler_b200', 'tests', 'oracle'):
   sys.path.insert(0, os.path.join(ROOT, sub))
 from soda import cuda as soda_cuda
